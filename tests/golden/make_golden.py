@@ -1,0 +1,290 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE.
+
+Run in the build container only (needs /root/reference, torch CPU):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or stored vectors of its own, so
+these files are "outputs of the reference itself run here": operator, RHS and
+mesh-converter results come from the imported reference modules
+(``operators``, ``rhs``, ``utility.utils``); the closures that live inside the
+reference's ``__main__`` blocks (``train2D.py:38-79``, ``operators.py:416-475``)
+cannot be imported and are bound here around those imported modules, line for
+line as the scripts do.  The fixtures pin ``oracle/ppnn_oracle.py``
+(tests/test_oracle_golden.py) and are compared directly with the CUDA path
+(tests/test_gpu_*.py).  Nothing reads /root/reference at test time.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("PPNN_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(REF, "src"))
+
+import operators as ref_ops          # noqa: E402  (reference module)
+import rhs as ref_rhs                # noqa: E402
+from utility.utils import mesh_convertor as ref_mesh   # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(1)             # deterministic reduction order
+
+
+def fourier_field(gen, b, n, shift=0.0):
+    """Smooth periodic [b,1,n,n] field with duplicated endpoint, like
+    operators.py:436-443 (81 modes, min-max normalised), then shifted."""
+    x = torch.linspace(0, 2 * np.pi, n)
+    x, y = torch.meshgrid(x, x, indexing="ij")
+    f = torch.zeros(b, 1, n, n)
+    for k in range(-4, 5):
+        for l in range(-4, 5):
+            f += torch.randn(b, 1, 1, 1, generator=gen) * torch.sin(k * x + l * y) \
+                + torch.randn(b, 1, 1, 1, generator=gen) * torch.cos(k * x + l * y)
+    lo, hi = f.amin(dim=(1, 2, 3), keepdim=True), f.amax(dim=(1, 2, 3), keepdim=True)
+    return (f - lo) / (hi - lo) + 0.1 - shift
+
+
+def save(name, **arrays):
+    out = {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+           for k, v in arrays.items()}
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(f"{name}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+# ---------------------------------------------------------------- operators
+def gen_operators():
+    g = torch.Generator().manual_seed(101)
+    u = torch.randn(2, 1, 19, 17, generator=g)
+    u[0, 0, 9, 8] = 0.0                        # an exact zero: '<= 0' branch
+    u1d = torch.randn(3, 1, 23, generator=g)
+    u1d[1, 0, 11] = 0.0
+    out = {"u2d": u, "u1d": u1d}
+    combos_d2 = [("Central2", a) for a in (2, 4, 6, 8)] + [("Central4", a) for a in (2, 4, 6)] \
+        + [("Forward1", 2), ("Backward1", 2)]
+    for scheme, acc in combos_d2:
+        out[f"d2udx2_2D/{scheme}/{acc}"] = ref_ops.d2udx2_2D(scheme, acc)(u)
+        out[f"d2udy2_2D/{scheme}/{acc}"] = ref_ops.d2udy2_2D(scheme, acc)(u)
+    combos_d1 = [("Upwind1", a) for a in (1, 2, 3)] + [("Central1", a) for a in (2, 4)] \
+        + [("Forward1", a) for a in (1, 2, 3)] + [("Backward1", a) for a in (1, 2, 3)] \
+        + [("Central2", 6), ("Central4", 4)]
+    for scheme, acc in combos_d1:
+        out[f"dudx_2D/{scheme}/{acc}"] = ref_ops.dudx_2D(scheme, acc)(u)
+        out[f"dudy_2D/{scheme}/{acc}"] = ref_ops.dudy_2D(scheme, acc)(u)
+    for scheme, accs in (("Central", (2, 4, 6, 8)), ("Central_4th", (2, 4, 6))):
+        for acc in accs:
+            out[f"diffusion1D/{scheme}/{acc}"] = ref_ops.diffusion1D(scheme, acc)(u1d)
+    for acc in (1, 2, 3):
+        out[f"dudx_1D/Upwind/{acc}"] = ref_ops.dudx_1D("Upwind", acc)(u1d)
+    save("operators.npz", **out)
+
+
+# ---------------------------------------------------------------- rhs
+def wrap(u, h, dim):
+    idx = [slice(None)] * 4
+    lo, hi = list(idx), list(idx)
+    lo[dim], hi[dim] = slice(-h, None), slice(None, h)
+    return torch.cat((u[tuple(lo)], u, u[tuple(hi)]), dim=dim)
+
+
+def gen_rhs():
+    g = torch.Generator().manual_seed(202)
+    n = 12
+    u1 = torch.randn(3, 1, n, n, generator=g)
+    v1 = torch.randn(3, 1, n, n, generator=g)
+    mu = torch.tensor([0.02, 0.045, 0.07]).reshape(-1, 1, 1, 1)
+    out = {"u1": u1, "v1": v1, "mu": mu}
+    names = [k for k in dir(ref_rhs) if not k.startswith("_") and k != "ks1d"]
+    out["names"] = np.array(names)
+    for (aa, da) in ((1, 2), (3, 6)):
+        h = aa
+        dudx, dudy = ref_ops.dudx_2D(accuracy=aa), ref_ops.dudy_2D(accuracy=aa)
+        d2x, d2y = ref_ops.d2udx2_2D(accuracy=da), ref_ops.d2udy2_2D(accuracy=da)
+        dx, dy = 0.1, 0.08
+        for name in names:
+            f = getattr(ref_rhs, name)
+            fld = v1 if name.endswith("v") else u1
+            out[f"{name}/{aa}{da}"] = f(u1, v1, mu, dudx, dudy, d2x, d2y,
+                                       wrap(fld, h, 2), wrap(fld, h, 3), dx, dy, dx ** 2, dy ** 2)
+    # 1-D Kuramoto-Sivashinsky (rhs.py:49-50): halo 2 for the 4th derivative
+    w = torch.randn(2, 1, 32, generator=g)
+    ux = torch.cat((w[:, :, -1:], w, w[:, :, :1]), dim=2)
+    ux4 = torch.cat((w[:, :, -2:], w, w[:, :, :2]), dim=2)
+    out["ks_w"] = w
+    out["ks1d"] = ref_rhs.ks1d(ux4, None, ref_ops.dudx_1D("Upwind", 1), ref_ops.diffusion1D("Central", 2),
+                               ref_ops.diffusion1D("Central_4th", 2), ux, 0.3, 0.09, 0.0081)
+    save("rhs.npz", **out)
+
+
+# ---------------------------------------------------------------- mesh
+def gen_mesh():
+    g = torch.Generator().manual_seed(303)
+    out = {}
+    f257 = fourier_field(g, 1, 257, shift=0.6)
+    out["f257"] = f257
+    for c in (33, 49):
+        m = ref_mesh(257, c, dim=2)
+        d = m.down(f257)
+        out[f"down/257/{c}"] = d
+        out[f"up/{c}/257"] = m.up(d)
+    r = torch.randn(2, 3, 65, 65, generator=g)
+    out["r65"] = r
+    for c in (17, 13, 9):
+        m = ref_mesh(65, c, dim=2)
+        d = m.down(r)
+        out[f"down/65/{c}"] = d
+        out[f"up/{c}/65"] = m.up(d)
+    rect = torch.randn(2, 1, 21, 30, generator=g)
+    out["rect"] = rect
+    m = ref_mesh((40, 57), (9, 13), dim=2)
+    out["rect_down"] = m.down(rect)
+    out["rect_up"] = m.up(rect)
+    for ac in (True, False):
+        m = ref_mesh(31, 7, dim=2, align_corners=ac)
+        s = torch.randn(1, 2, 31, 31, generator=g)
+        out[f"ac{int(ac)}_in"] = s
+        d = m.down(s)
+        out[f"ac{int(ac)}_down"] = d
+        out[f"ac{int(ac)}_up"] = m.up(d)
+    m1 = ref_mesh(101, 11, dim=1)
+    l = torch.randn(2, 1, 101, generator=g)
+    out["line"] = l
+    out["line_down"] = m1.down(l)
+    out["line_up"] = m1.up(m1.down(l))
+    save("mesh.npz", **out)
+
+
+# ---------------------------------------------------------------- pde_du
+def make_pde_du(fine, cmesh, rhsu_name, rhsv_name, dt, length):
+    """train2D.py:38-79 bound around the imported reference modules."""
+    def padbcx(uinner):
+        return torch.cat((uinner[:, :, -1:], uinner, uinner[:, :, :1]), dim=2)
+
+    def padbcy(uinner):
+        return torch.cat((uinner[:, :, :, -1:], uinner, uinner[:, :, :, :1]), dim=3)
+
+    def padBC_rd(u):
+        tmp = torch.cat((u, u[:, :, :, :1]), dim=3)
+        return torch.cat((tmp, tmp[:, :, :1]), dim=2)
+
+    rhsu, rhsv = getattr(ref_rhs, rhsu_name), getattr(ref_rhs, rhsv_name)
+    d2udx2 = ref_ops.d2udx2_2D(accuracy=2)
+    d2udy2 = ref_ops.d2udy2_2D(accuracy=2)
+    dudx = ref_ops.dudx_2D(accuracy=1)
+    dudy = ref_ops.dudy_2D(accuracy=1)
+    dx = length / (cmesh - 1)
+    mcvter = ref_mesh(fine, cmesh, dim=2)
+    dx2 = dx ** 2
+    dy, dy2 = dx, dx2
+
+    def pde_du(u, mu):
+        u1 = mcvter.down(u[:, :1])[:, :, :-1, :-1]
+        v1 = mcvter.down(u[:, 1:])[:, :, :-1, :-1]
+        ux, uy, vx, vy = padbcx(u1), padbcy(u1), padbcx(v1), padbcy(v1)
+        return torch.cat((mcvter.up(padBC_rd(dt * rhsu(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, ux, uy, dx, dy, dx2, dy2))),
+                          mcvter.up(padBC_rd(dt * rhsv(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, vx, vy, dx, dy, dx2, dy2)))),
+                         dim=1)
+    return pde_du, padBC_rd
+
+
+# the three BASELINE cases (cases/burgers_pPDE.yaml, RD_pPDE.yaml, burgers_fPDE.yaml)
+CASES = {
+    "burgers_p": dict(cmesh=33, rhsu="burgers2Dpu", rhsv="burgers2Dpv", dt=0.02, length=3.2, mu=(0.02, 0.07)),
+    "rd_p": dict(cmesh=49, rhsu="rdpu", rhsv="rdpv", dt=0.002, length=6.4, mu=(0.2, 1.3)),
+    "burgers_f": dict(cmesh=49, rhsu="burgers2DFu", rhsv="burgers2DFv", dt=0.02, length=3.2, mu=(0.02, 0.07)),
+    "rd_f": dict(cmesh=49, rhsu="rdFu", rhsv="rdFv", dt=0.002, length=6.4, mu=(0.2, 1.3)),
+}
+# small analogues with the same mesh ratios: 64/8 = 8 (decimation) and 64/12 = 16/3
+SMALL = {"burgers_p": 9, "rd_p": 13, "burgers_f": 13, "rd_f": 13}
+
+
+def gen_pde_du():
+    g = torch.Generator().manual_seed(404)
+    u257 = torch.cat((fourier_field(g, 1, 257, 0.6), fourier_field(g, 1, 257, 0.6)), dim=1)
+    out = {"u257": u257}
+    for name, c in CASES.items():
+        f, _ = make_pde_du(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+        mu = torch.tensor([c["mu"][1]]).reshape(1, 1, 1, 1)
+        out[f"{name}/257"] = f(u257, mu)
+    save("pde_du_257.npz", **out)
+
+    out = {}
+    b = 3
+    u65 = torch.cat((fourier_field(g, b, 65, 0.6), fourier_field(g, b, 65, 0.6)), dim=1)
+    u65[2] += 0.6                                       # one all-positive sample
+    out["u65"] = u65
+    cot = torch.randn(b, 2, 65, 65, generator=g)
+    out["cot65"] = cot
+    nn_out = torch.randn(b, 2, 64, 64, generator=g)
+    out["nn65"] = nn_out
+    stats = {"outmean": torch.tensor([0.01, -0.02]).reshape(1, 2, 1, 1),
+             "outstd": torch.tensor([0.3, 0.2]).reshape(1, 2, 1, 1)}
+    out.update(stats)
+    for name, c in CASES.items():
+        cm = SMALL[name]
+        length = c["length"] * (cm - 1) / (c["cmesh"] - 1) * 0.5   # keep dx in a stable range
+        f, padBC_rd = make_pde_du(65, cm, c["rhsu"], c["rhsv"], c["dt"], length)
+        mu = torch.linspace(c["mu"][0], c["mu"][1], b).reshape(-1, 1, 1, 1)
+        out[f"{name}/length"] = length
+        out[f"{name}/mu"] = mu
+        uu = u65.clone().requires_grad_(True)
+        mm = mu.clone().requires_grad_(True)
+        y = f(uu, mm)
+        out[f"{name}/pdeu"] = y
+        gu, gm = torch.autograd.grad(y, (uu, mm), cot)
+        out[f"{name}/grad_u"] = gu
+        out[f"{name}/grad_mu"] = gm
+        # train2D.py:235-238 with a stand-in network output
+        out[f"{name}/update"] = padBC_rd(nn_out * stats["outstd"] + stats["outmean"]) + u65 + y.detach()
+        # PDE-only rollout, post_process/test_predict_2Dp.py:116
+        w = u65.clone()
+        for _ in range(5):
+            w = w + f(w, mu)
+        out[f"{name}/rollout5"] = w
+    save("pde_du_65.npz", **out)
+
+
+# ---------------------------------------------------------------- fine solver
+def gen_fine():
+    """operators.py:416-420,450-455,466-475 around the imported modules."""
+    g = torch.Generator().manual_seed(505)
+    n, b = 33, 4
+    mu = torch.linspace(0.025, 0.065, b).reshape(-1, 1, 1, 1)
+    u0 = fourier_field(g, b, n, 0.0)
+    v0 = fourier_field(g, b, n, 0.0)
+    u0[2:] -= 0.6                                       # mixed-sign samples
+    v0[2:] -= 0.6
+    dt, dx, dy = 1e-4, 0.0125, 0.0125
+    dx2, dy2 = dx ** 2, dy ** 2
+    dudx, dudy = ref_ops.dudx_2D("Upwind1", accuracy=3), ref_ops.dudy_2D("Upwind1", accuracy=3)
+    d2udx2, d2udy2 = ref_ops.d2udx2_2D("Central2", accuracy=6), ref_ops.d2udy2_2D("Central2", accuracy=6)
+
+    def padbcx(uinner):
+        return torch.cat((uinner[:, :, -4:-1], uinner, uinner[:, :, 1:4]), dim=2)
+
+    def padbcy(uinner):
+        return torch.cat((uinner[:, :, :, -4:-1], uinner, uinner[:, :, :, 1:4]), dim=3)
+
+    out = {"u0": u0, "v0": v0, "mu": mu}
+    for mode in ("as_written", "intended"):
+        u, v = u0.clone(), v0.clone()
+        for i in range(4):
+            ux, uy, vx, vy = padbcx(u), padbcy(u), padbcx(v), padbcy(v)
+            u = u + dt * ref_rhs.burgers2Dpu(u, v, mu, dudx, dudy, d2udx2, d2udy2, ux, uy, dx, dy, dx2, dy2)
+            if mode == "as_written":                     # the live line, operators.py:475
+                v = v + dt * ref_rhs.burgers2Dpv(u, v, mu, dudx, dudy, d2udx2, d2udy2, ux, uy, dx, dy, dx2, dy2)
+            else:                                        # the commented formula on that line
+                v = v + dt * ref_rhs.burgers2Dpv(u, v, mu, dudx, dudy, d2udx2, d2udy2, vx, vy, dx, dy, dx2, dy2)
+            if i in (0, 3):
+                out[f"{mode}/u{i + 1}"] = u
+                out[f"{mode}/v{i + 1}"] = v
+    save("fine.npz", **out)
+
+
+if __name__ == "__main__":
+    gen_operators()
+    gen_rhs()
+    gen_mesh()
+    gen_pde_du()
+    gen_fine()

@@ -1,0 +1,141 @@
+"""Pin the CPU oracle against outputs of the reference itself
+(tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import ppnn_oracle as O
+from conftest import assert_parity, load_golden
+
+TOL = 2e-6     # same ATen ops in the same order; only thread-count / blocking may differ
+
+
+def test_operator_tables_and_ops():
+    g = load_golden("operators.npz")
+    u, u1d = g["u2d"], g["u1d"]
+    n = 0
+    for key, ref in g.items():
+        if "/" not in key:
+            continue
+        cls, scheme, acc = key.split("/")
+        acc = int(acc)
+        if cls.endswith("_2D"):
+            axis = 2 if cls in ("dudx_2D", "d2udx2_2D") else 3
+            ours = O.stencil2d(u, scheme, acc, axis)
+        else:
+            ours = O.stencil1d(u1d, scheme, acc)
+        assert_parity(ours, ref, TOL, key)
+        n += 1
+    assert n == 54
+
+
+def test_rhs_all_names():
+    g = load_golden("rhs.npz")
+    u1, v1, mu = g["u1"], g["v1"], g["mu"]
+    names = [str(s) for s in g["names"]]
+    assert sorted(names) == sorted(O.RHS_NAMES_2D)
+    for aa, da in ((1, 2), (3, 6)):
+        o = O.Ops(adv_accuracy=aa, diff_accuracy=da)
+        for name in names:
+            fld = v1 if name.endswith("v") else u1
+            ours = O.rhs(name, u1, v1, mu, o, O.wrap_x(fld, aa), O.wrap_y(fld, aa), 0.1, 0.08, 0.1 ** 2, 0.08 ** 2)
+            assert_parity(ours, g[f"{name}/{aa}{da}"], TOL, f"{name}/{aa}{da}")
+    w = g["ks_w"]
+    ours = O.ks1d(torch.cat((w[:, :, -2:], w, w[:, :, :2]), 2), None,
+                  torch.cat((w[:, :, -1:], w, w[:, :, :1]), 2), 0.3, 0.09, 0.0081)
+    assert_parity(ours, g["ks1d"], TOL, "ks1d")
+
+
+def test_mesh_converter():
+    g = load_golden("mesh.npz")
+    for c in (33, 49):
+        d = O.mesh_down(g["f257"], c)
+        assert_parity(d, g[f"down/257/{c}"], TOL, f"down 257->{c}")
+        assert_parity(O.mesh_up(d, 257), g[f"up/{c}/257"], TOL, f"up {c}->257")
+    for c in (17, 13, 9):
+        d = O.mesh_down(g["r65"], c)
+        assert_parity(d, g[f"down/65/{c}"], TOL, f"down 65->{c}")
+        assert_parity(O.mesh_up(d, 65), g[f"up/{c}/65"], TOL, f"up {c}->65")
+    assert_parity(O.mesh_down(g["rect"], (9, 13)), g["rect_down"], TOL, "rect down")
+    assert_parity(O.mesh_up(g["rect"], (40, 57)), g["rect_up"], TOL, "rect up")
+    for ac in (1, 0):
+        d = O.mesh_down(g[f"ac{ac}_in"], 7, align_corners=bool(ac))
+        assert_parity(d, g[f"ac{ac}_down"], TOL, f"ac{ac} down")
+        assert_parity(O.mesh_up(d, 31, align_corners=bool(ac)), g[f"ac{ac}_up"], TOL, f"ac{ac} up")
+    d = O.mesh_down(g["line"], 11)
+    assert_parity(d, g["line_down"], TOL, "1-D down")
+    assert_parity(O.mesh_up(d, 101), g["line_up"], TOL, "1-D up")
+
+
+def test_closed_form_interpolation_matrices():
+    """bilinear / Keys-cubic (A=-0.75, clamped) closed forms."""
+    for n_in, n_out in ((257, 33), (257, 49), (65, 13)):
+        x = torch.randn(1, 1, n_in, n_in, dtype=torch.float64)
+        m = torch.from_numpy(O.bilinear_matrix(n_in, n_out))
+        assert (m @ x[0, 0] @ m.T - O.mesh_down(x, n_out)[0, 0]).abs().max() < 1e-13
+    for n_in, n_out in ((33, 257), (49, 257), (13, 65)):
+        x = torch.randn(1, 1, n_in, n_in, dtype=torch.float64)
+        m = torch.from_numpy(O.bicubic_matrix(n_in, n_out))
+        assert (m @ x[0, 0] @ m.T - O.mesh_up(x, n_out)[0, 0]).abs().max() < 1e-13
+
+
+CASES = {
+    "burgers_p": dict(cmesh=33, rhsu="burgers2Dpu", rhsv="burgers2Dpv", dt=0.02, length=3.2, mu=0.07),
+    "rd_p": dict(cmesh=49, rhsu="rdpu", rhsv="rdpv", dt=0.002, length=6.4, mu=1.3),
+    "burgers_f": dict(cmesh=49, rhsu="burgers2DFu", rhsv="burgers2DFv", dt=0.02, length=3.2, mu=0.07),
+    "rd_f": dict(cmesh=49, rhsu="rdFu", rhsv="rdFv", dt=0.002, length=6.4, mu=1.3),
+}
+SMALL = {"burgers_p": 9, "rd_p": 13, "burgers_f": 13, "rd_f": 13}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_pde_du_full_size(case):
+    g = load_golden("pde_du_257.npz")
+    c = CASES[case]
+    step = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    mu = torch.tensor([c["mu"]]).reshape(1, 1, 1, 1)
+    assert_parity(step.pde_du(g["u257"], mu), g[f"{case}/257"], TOL, case)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_pde_du_small_with_grads_update_rollout(case):
+    g = load_golden("pde_du_65.npz")
+    c = CASES[case]
+    step = O.CoarseStep(65, SMALL[case], c["rhsu"], c["rhsv"], c["dt"], float(g[f"{case}/length"]))
+    mu = g[f"{case}/mu"]
+    u = g["u65"].clone().requires_grad_(True)
+    m = mu.clone().requires_grad_(True)
+    y = step.pde_du(u, m)
+    assert_parity(y.detach(), g[f"{case}/pdeu"], TOL, case + " pdeu")
+    gu, gm = torch.autograd.grad(y, (u, m), g["cot65"], allow_unused=True)
+    assert_parity(gu, g[f"{case}/grad_u"], TOL, case + " grad_u")
+    if gm is not None and g[f"{case}/grad_mu"].abs().max() > 0:
+        assert_parity(gm, g[f"{case}/grad_mu"], 2e-5, case + " grad_mu")
+    upd = O.ppnn_update(g["u65"], y.detach(), g["nn65"], g["outmean"], g["outstd"])
+    assert_parity(upd, g[f"{case}/update"], TOL, case + " update")
+    roll = O.pde_only_rollout(step, g["u65"], mu, 5)[-1]
+    assert_parity(roll, g[f"{case}/rollout5"], TOL, case + " rollout5")
+
+
+@pytest.mark.parametrize("mode", ["as_written", "intended"])
+def test_fine_solver(mode):
+    g = load_golden("fine.npz")
+    u, v = g["u0"], g["v0"]
+    for i in range(4):
+        u, v = O.fine_burgers_step(u, v, g["mu"], mode=mode)
+        if i in (0, 3):
+            assert_parity(u, g[f"{mode}/u{i + 1}"], TOL, f"{mode} u{i + 1}")
+            assert_parity(v, g[f"{mode}/v{i + 1}"], TOL, f"{mode} v{i + 1}")
+
+
+def test_fine_solver_q3_quirk_is_real():
+    """as_written and intended must differ, or the fixture is vacuous."""
+    g = load_golden("fine.npz")
+    assert (g["as_written/v4"] - g["intended/v4"]).abs().max() > 1e-6
+
+
+def test_fourier_ic_range():
+    coef = torch.randn(2, 81, 2)
+    f = O.fourier_initial_condition(coef, 33)
+    assert f.shape == (2, 1, 33, 33)
+    assert abs(f.min().item() - 0.1) < 1e-6 and abs(f.max().item() - 1.1) < 1e-6

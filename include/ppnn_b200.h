@@ -1,0 +1,174 @@
+/* ppnn_b200.h -- C ABI of libppnn_b200.so: the PDE-preserving hot path of PPNN
+ * (jx-wang-s-group/ppnn) as hand-written sm_100a CUDA kernels.
+ *
+ * Contract:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 owned by the caller;
+ *     the library never allocates, frees or retains memory and keeps no state;
+ *   - every entry enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising; entries are re-entrant and graph-capturable;
+ *   - return value: 0 = ok, negative = PPNN_E_* (bad argument, nothing launched),
+ *     positive = the cudaError_t reported by the launch;
+ *   - "x" is tensor dim 2 (H, rows) and "y" is dim 3 (W, columns), as in the
+ *     reference (src/operators.py:194-198 builds x-filters by permuting y-filters).
+ *
+ * Each entry names the reference interface it replaces (paths relative to the
+ * reference checkout).
+ */
+#ifndef PPNN_B200_H
+#define PPNN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPNN_B200_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------- */
+#define PPNN_OK            0
+#define PPNN_E_NULL       -1   /* required pointer is NULL                    */
+#define PPNN_E_SHAPE      -2   /* non-positive or inconsistent sizes          */
+#define PPNN_E_SCHEME     -3   /* unknown scheme / accuracy combination       */
+#define PPNN_E_RHS        -4   /* unknown right-hand-side id                  */
+#define PPNN_E_TOOBIG     -5   /* coarse grid does not fit in shared memory   */
+#define PPNN_E_MODE       -6   /* unknown mode / flag value                   */
+#define PPNN_E_HALO       -7   /* pre-padded halo does not match the stencils */
+
+/* ---- finite-difference schemes (src/operators.py:58-61,200-218) ----------- */
+enum ppnn_scheme {
+    PPNN_CENTRAL1  = 0,   /* 'Central1'  d/dx,    accuracy 2,4                 */
+    PPNN_CENTRAL2  = 1,   /* 'Central2'  d2/dx2,  accuracy 2,4,6,8 (1-D: 'Central')     */
+    PPNN_CENTRAL4  = 2,   /* 'Central4'  d4/dx4,  accuracy 2,4,6   (1-D: 'Central_4th') */
+    PPNN_FORWARD1  = 3,   /* 'Forward1'  accuracy 1,2,3                        */
+    PPNN_BACKWARD1 = 4,   /* 'Backward1' accuracy 1,2,3                        */
+    PPNN_UPWIND1   = 5    /* 'Upwind1'   accuracy 1,2,3 (1-D: 'Upwind'); switch on sign of the field */
+};
+
+/* ---- right-hand sides (src/rhs.py) ---------------------------------------- *
+ * id = PPNN_RHS_ADV | PPNN_RHS_DIFF | reaction term.  The sixteen 2-D names of
+ * rhs.py map onto these nine ids (ppnn_b200/rhs.py holds the table).           */
+#define PPNN_RHS_ADV      1    /* -u1*dudx(a)/dx - v1*dudy(a)/dy   rhs.py:43-47 */
+#define PPNN_RHS_DIFF     2    /* mu*(d2udx2(a)/dx2+d2udy2(a)/dy2) rhs.py:17-23 */
+#define PPNN_REACT_NONE   0
+#define PPNN_REACT_BFU    4    /* + (1-uv)*u1 + uv*v1              rhs.py:1-3   */
+#define PPNN_REACT_BFV    8    /* - uv*u1 + (1-uv)*v1              rhs.py:5-7   */
+#define PPNN_REACT_RDU   12    /* + u1 - u1^3 - v1 + 0.01          rhs.py:25-26,52-53 */
+#define PPNN_REACT_RDV   16    /* + 0.25*(u1 - v1)                 rhs.py:28-29,55-56 */
+
+/* ---- resampling modes (src/utility/utils.py:13-31) ------------------------ */
+#define PPNN_BILINEAR 0        /* mesh_convertor.down (also 'linear' with H=1) */
+#define PPNN_BICUBIC  1        /* mesh_convertor.up   (Keys A=-0.75, clamped)  */
+
+/* ---- fine solver modes (src/operators.py:474-475) -------- */
+#define PPNN_FINE_AS_WRITTEN 0 /* v update sees the updated u and u's halos    */
+#define PPNN_FINE_INTENDED   1 /* the commented formula: v's own halos         */
+
+int         ppnn_abi_version(void);
+const char* ppnn_status_string(int status);
+
+/* =========================== Tier A: operator API ========================== */
+
+/* d2udx2_2D / d2udy2_2D / dudx_2D / dudy_2D.__call__ (src/operators.py:236-237,
+ * 246-247, 255-260, 268-273): 'valid' cross-correlation of `planes` single-
+ * channel images [Hin, Win] along `axis` (2 = x/H, 3 = y/W).  Output is
+ * [Hin-K+1, Win] or [Hin, Win-K+1], K = number of taps (2a+1 for Upwind1).
+ * With Hin = 1, axis = 3 this is diffusion1D / dudx_1D (operators.py:85,126).  */
+int ppnn_stencil_fwd(const float* in, float* out, long planes, int Hin, int Win,
+                     int axis, int scheme, int accuracy, void* stream);
+
+/* adjoint of the above w.r.t. `in` (what autograd derives from conv2d and the
+ * comparison masks).  `in` is only read for PPNN_UPWIND1 (may be NULL otherwise).
+ * grad_in has the padded shape [Hin, Win] and is fully overwritten.            */
+int ppnn_stencil_bwd(const float* grad_out, const float* in, float* grad_in,
+                     long planes, int Hin, int Win, int axis, int scheme,
+                     int accuracy, void* stream);
+
+/* One rhs.py function on the caller's pre-padded halos (src/rhs.py:1-47,52-56):
+ * u1, v1, out are [B, H, W]; ax is [B, H+2h, W], ay is [B, H, W+2h]; mu is [B].
+ * adv_*: scheme/accuracy of dudx and dudy; diff_*: of d2udx2 and d2udy2; both
+ * must need the same halo h (as the reference's single pad implies).           */
+int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
+                   const float* ax, const float* ay, float* out,
+                   int B, int H, int W, int halo, int rhs_id,
+                   int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
+                   float dx, float dy, float dx2, float dy2, void* stream);
+
+/* mesh_convertor.down / .up (src/utility/utils.py:24,27-31): torch
+ * F.interpolate(mode='bilinear'|'bicubic', size=(Hout,Wout), align_corners).    */
+int ppnn_resample_fwd(const float* in, float* out, long planes, int Hin, int Win,
+                      int Hout, int Wout, int mode, int align_corners, void* stream);
+/* adjoint w.r.t. `in`; grad_in [planes,Hin,Win] is zero-filled then accumulated. */
+int ppnn_resample_bwd(const float* grad_out, float* grad_in, long planes, int Hin, int Win,
+                      int Hout, int Wout, int mode, int align_corners, void* stream);
+
+/* ====================== Tier B: fused coarse-grid step ===================== */
+
+/* Geometry and physics of one YAML case (src/train2D.py:49-64).               */
+typedef struct ppnn_coarse_cfg {
+    int   FH, FW;            /* fine mesh incl. duplicated endpoint (finemeshsize)   */
+    int   CH, CW;            /* coarse mesh incl. duplicated endpoint (coarsemeshsize) */
+    int   rhs_u, rhs_v;      /* PPNN_RHS_* | PPNN_REACT_*  (rhsu / rhsv)             */
+    int   adv_accuracy;      /* Upwind1 accuracy of dudx/dudy (train2D.py:55-56: 1)  */
+    int   diff_accuracy;     /* Central2 accuracy of d2udx2/d2udy2 (train2D.py:53-54: 2) */
+    float dt, dx, dy, dx2, dy2;
+} ppnn_coarse_cfg;
+
+/* pde_du (src/train2D.py:66-79): u [B,2,FH,FW], mu [B] -> pdeu [B,2,FH,FW].    */
+int ppnn_pde_du_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                    float* pdeu, int B, void* stream);
+
+/* Vector-Jacobian product of pde_du: grad_u [B,2,FH,FW] (overwritten) and
+ * grad_mu [B] (overwritten; may be NULL).  add_identity != 0 returns
+ * grad_out + J^T grad_out, the adjoint of  u -> u + pde_du(u).                  */
+int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                    const float* grad_out, float* grad_u, float* grad_mu,
+                    int B, int add_identity, void* stream);
+
+/* Network inputs of one rollout step (src/train2D.py:235-237), fused with pde_du:
+ *   u_norm    [B,2,FH-1,FW-1] = (u[:,:,:-1,:-1]      - inmean ) / instd
+ *   pdeu_norm [B,2,FH-1,FW-1] = (pde_du(u)[:,:,:-1,:-1] - pdemean) / pdestd
+ * stats are per-channel pairs {c0, c1}.  pdeu_norm may be NULL (cnn2d ignores it,
+ * src/models.py:95-96); pdeu (un-normalised, full [B,2,FH,FW]) may be NULL.     */
+int ppnn_step_inputs(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                     const float* inmean, const float* instd,
+                     const float* pdemean, const float* pdestd,
+                     float* u_norm, float* pdeu_norm, float* pdeu, int B, void* stream);
+
+/* The explicit update of one rollout step (src/train2D.py:235-238), fused with
+ * pde_du:  u_next = padBC_rd(nn_out*outstd + outmean) + u + pde_du(u, mu).
+ * nn_out [B,2,FH-1,FW-1] may be NULL: u_next = u + pde_du(u)  (the PDE-only
+ * rollout of post_process/test_predict_2Dp.py:116).  u_next may alias u.        */
+int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                     const float* nn_out, const float* outmean, const float* outstd,
+                     float* u_next, int B, void* stream);
+
+/* Coarse-only solver increment (post_process/test_2D_csolver.py:56-66): the state
+ * lives on the coarse grid, uc [B,2,CH,CW]; out = padBC_rd(dt*rhs) (add_state=0)
+ * or uc + padBC_rd(dt*rhs) (add_state=1).  FH/FW of cfg are ignored.            */
+int ppnn_coarse_increment(const ppnn_coarse_cfg* cfg, const float* uc, const float* mu,
+                          float* out, int B, int add_state, void* stream);
+
+/* ===================== Tier B: fine-grid explicit solver =================== */
+
+/* One explicit Euler step of the 2-D Burgers generator (src/operators.py:466-475)
+ * on u, v [B,H,W] with mu [B]:  Upwind1(adv_accuracy) + Central2(diff_accuracy).
+ * endpoint != 0: the grid carries a duplicated periodic endpoint (period H-1 /
+ * W-1, operators.py:416-420); endpoint == 0: true periodic (period H / W).
+ * mode: PPNN_FINE_AS_WRITTEN | PPNN_FINE_INTENDED.  Outputs must not alias inputs. */
+int ppnn_fine_burgers_step(const float* u, const float* v, const float* mu,
+                           float* u_out, float* v_out, int B, int H, int W,
+                           int endpoint, int mode, int adv_accuracy, int diff_accuracy,
+                           float dt, float dx, float dy, void* stream);
+
+/* Generic fused explicit step  f <- f + dt*rhs(f)  for any rhs id pair on a
+ * periodic fine grid (the commented generators of operators.py:494-748: RD,
+ * diffusion, convection); Jacobi update (both fields from the old state).      */
+int ppnn_fine_rhs_step(const float* u, const float* v, const float* mu,
+                       float* u_out, float* v_out, int B, int H, int W,
+                       int endpoint, int rhs_u, int rhs_v,
+                       int adv_accuracy, int diff_accuracy,
+                       float dt, float dx, float dy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPNN_B200_H */

@@ -1,0 +1,139 @@
+// Tier A: mesh_convertor.down / .up (src/utility/utils.py:13-31) as stand-alone
+// kernels: torch F.interpolate(mode='bilinear' | 'bicubic', size=..., align_corners)
+// semantics -- source index = scale * o (align_corners) or scale*(o+.5)-.5,
+// bilinear weights (1-t, t) with the +1 neighbour dropped at the border, Keys
+// cubic A = -0.75 with taps clamped to the border.  Forward is
+// a gather (thread per output, coalesced stores); the adjoint scatters with
+// atomics into a zero-filled grad_in, as torch's own CUDA backward does.
+#include "common.cuh"
+
+namespace ppnn {
+
+struct ResampleParams {
+    const float* in; float* out;
+    int Hin, Win, Hout, Wout;
+    int align;
+    float sh, sw;
+    long total;     // planes * Hout * Wout
+};
+
+template <int MODE, bool BWD>
+__global__ void __launch_bounds__(256)
+resample_kernel(const ResampleParams p) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long)gridDim.x * blockDim.x) {
+        int j = (int)(idx % p.Wout);
+        long t = idx / p.Wout;
+        int i = (int)(t % p.Hout);
+        long pl = t / p.Hout;
+        size_t base = (size_t)pl * p.Hin * p.Win;
+        float g = BWD ? __ldg(p.in + idx) : 0.f;        // BWD: `in` is grad_out, `out` is grad_in
+        if (MODE == PPNN_BILINEAR) {
+            float si = resample_src(p.sh, i, p.align, false), sj = resample_src(p.sw, j, p.align, false);
+            int i0 = min((int)si, p.Hin - 1), j0 = min((int)sj, p.Win - 1);
+            int di = i0 < p.Hin - 1 ? 1 : 0, dj = j0 < p.Win - 1 ? 1 : 0;
+            float li = si - (float)i0, lj = sj - (float)j0;
+            float h0 = 1.f - li, w0 = 1.f - lj;
+            size_t o00 = base + (size_t)i0 * p.Win + j0;
+            size_t o01 = o00 + dj, o10 = o00 + (size_t)di * p.Win, o11 = o10 + dj;
+            if (!BWD) {
+                const float* q = p.in;
+                float v = h0 * (w0 * __ldg(q + o00) + lj * __ldg(q + o01)) +
+                          li * (w0 * __ldg(q + o10) + lj * __ldg(q + o11));
+                st_stream(p.out + idx, v);
+            } else {
+                atomicAdd(p.out + o00, h0 * w0 * g);
+                atomicAdd(p.out + o01, h0 * lj * g);
+                atomicAdd(p.out + o10, li * w0 * g);
+                atomicAdd(p.out + o11, li * lj * g);
+            }
+        } else {
+            float si = resample_src(p.sh, i, p.align, true), sj = resample_src(p.sw, j, p.align, true);
+            float fi = floorf(si), fj = floorf(sj);
+            int i0 = (int)fi, j0 = (int)fj;
+            float wi[4], wj[4];
+            cubic_weights(si - fi, wi);
+            cubic_weights(sj - fj, wj);
+            int cj[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cj[k] = clampi(j0 - 1 + k, 0, p.Win - 1);
+            float v = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                size_t row = base + (size_t)clampi(i0 - 1 + a, 0, p.Hin - 1) * p.Win;
+                if (!BWD) {
+                    const float* q = p.in + row;
+                    // W pass then H pass, like torch's cubic_interp1d nesting
+                    float r = __ldg(q + cj[0]) * wj[0] + __ldg(q + cj[1]) * wj[1] +
+                              __ldg(q + cj[2]) * wj[2] + __ldg(q + cj[3]) * wj[3];
+                    v += r * wi[a];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) atomicAdd(p.out + row + cj[k], wi[a] * wj[k] * g);
+                }
+            }
+            if (!BWD) st_stream(p.out + idx, v);
+        }
+    }
+}
+
+static int run_resample(const float* in, float* out, long planes, int Hin, int Win, int Hout, int Wout,
+                        int mode, int align, bool bwd, void* stream) {
+    if (!in || !out) return PPNN_E_NULL;
+    if (planes < 0 || Hin < 1 || Win < 1 || Hout < 1 || Wout < 1) return PPNN_E_SHAPE;
+    if (mode != PPNN_BILINEAR && mode != PPNN_BICUBIC) return PPNN_E_MODE;
+    if (planes == 0) return PPNN_OK;
+    ResampleParams p;
+    p.in = in; p.out = out; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout;
+    p.align = align != 0;
+    p.sh = resample_scale(Hin, Hout, p.align);
+    p.sw = resample_scale(Win, Wout, p.align);
+    p.total = planes * Hout * Wout;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bwd) {
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)planes * Hin * Win * sizeof(float), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    long blocks = (p.total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    unsigned g = (unsigned)blocks;
+    if (mode == PPNN_BILINEAR) {
+        if (bwd) resample_kernel<PPNN_BILINEAR, true><<<g, 256, 0, s>>>(p);
+        else     resample_kernel<PPNN_BILINEAR, false><<<g, 256, 0, s>>>(p);
+    } else {
+        if (bwd) resample_kernel<PPNN_BICUBIC, true><<<g, 256, 0, s>>>(p);
+        else     resample_kernel<PPNN_BICUBIC, false><<<g, 256, 0, s>>>(p);
+    }
+    return launch_status();
+}
+
+}  // namespace ppnn
+
+using namespace ppnn;
+
+extern "C" int ppnn_resample_fwd(const float* in, float* out, long planes, int Hin, int Win,
+                                 int Hout, int Wout, int mode, int align_corners, void* stream) {
+    return run_resample(in, out, planes, Hin, Win, Hout, Wout, mode, align_corners, false, stream);
+}
+
+extern "C" int ppnn_resample_bwd(const float* grad_out, float* grad_in, long planes, int Hin, int Win,
+                                 int Hout, int Wout, int mode, int align_corners, void* stream) {
+    return run_resample(grad_out, grad_in, planes, Hin, Win, Hout, Wout, mode, align_corners, true, stream);
+}
+
+extern "C" int ppnn_abi_version(void) { return PPNN_B200_ABI_VERSION; }
+
+extern "C" const char* ppnn_status_string(int status) {
+    switch (status) {
+    case PPNN_OK: return "ok";
+    case PPNN_E_NULL: return "required pointer is NULL";
+    case PPNN_E_SHAPE: return "non-positive or inconsistent sizes";
+    case PPNN_E_SCHEME: return "unknown scheme / accuracy combination";
+    case PPNN_E_RHS: return "unknown right-hand-side id";
+    case PPNN_E_TOOBIG: return "coarse grid does not fit in shared memory";
+    case PPNN_E_MODE: return "unknown mode / flag value";
+    case PPNN_E_HALO: return "halo does not match the stencils";
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown status";
+}

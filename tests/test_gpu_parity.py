@@ -1,0 +1,414 @@
+"""Parity of the CUDA path (through the C ABI) against the committed golden
+vectors of the reference (tests/golden/*.npz) and against the CPU oracle on the
+same seeded inputs.  Metric and tolerance: SURVEY.md 8(c) -- rel-L2 <= 1e-5 and
+max-abs / ||ref||_inf <= 1e-5 per step, fp32.  All tests need a B200."""
+import math
+
+import pytest
+import torch
+
+import ppnn_oracle as O
+from conftest import assert_parity, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import ppnn_b200
+    import ppnn_b200.operators as ops
+    import ppnn_b200.rhs as rhs
+    from ppnn_b200.utility.utils import mesh_convertor
+    from ppnn_b200 import _lib
+    _lib.load()
+    return dict(ops=ops, rhs=rhs, mesh=mesh_convertor, CoarseStep=ppnn_b200.CoarseStep,
+                FineBurgers=ppnn_b200.FineBurgers, lib=_lib)
+
+
+def cu(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+# --------------------------------------------------------------------- Tier A
+def _make_op(ops, cls, scheme, acc):
+    return getattr(ops, cls)(scheme, acc, device="cuda")
+
+
+def test_operators_against_reference_golden(pk):
+    g = load_golden("operators.npz")
+    u, u1d = g["u2d"].cuda(), g["u1d"].cuda()
+    n = 0
+    for key, ref in g.items():
+        if "/" not in key:
+            continue
+        cls, scheme, acc = key.split("/")
+        op = _make_op(pk["ops"], cls, scheme, int(acc))
+        ours = op(u if cls.endswith("_2D") else u1d)
+        assert_parity(ours.cpu(), ref, TOL, key)
+        n += 1
+    assert n == 54
+
+
+def test_operator_adjoints_match_autograd_of_the_oracle(pk):
+    gen = torch.Generator().manual_seed(7)
+    u = torch.randn(3, 1, 23, 21, generator=gen)
+    u[0, 0, 11, 10] = 0.0
+    u1d = torch.randn(2, 1, 37, generator=gen)
+    cases = [("d2udx2_2D", "Central2", a, 2) for a in (2, 4, 6, 8)] + \
+            [("d2udy2_2D", "Central4", a, 3) for a in (2, 4, 6)] + \
+            [("dudx_2D", "Upwind1", a, 2) for a in (1, 2, 3)] + \
+            [("dudy_2D", "Upwind1", a, 3) for a in (1, 2, 3)] + \
+            [("dudx_2D", "Central1", 4, 2), ("dudy_2D", "Forward1", 3, 3), ("dudx_2D", "Backward1", 2, 2)]
+    for cls, scheme, acc, axis in cases:
+        x = u.clone().requires_grad_(True)
+        y = O.stencil2d(x, scheme, acc, axis)
+        cot = torch.randn(y.shape, generator=gen)
+        (gref,) = torch.autograd.grad(y, x, cot)
+        xc = u.cuda().requires_grad_(True)
+        yc = _make_op(pk["ops"], cls, scheme, acc)(xc)
+        (gours,) = torch.autograd.grad(yc, xc, cot.cuda())
+        assert_parity(yc.detach().cpu(), y.detach(), TOL, f"{cls}/{scheme}/{acc} fwd")
+        assert_parity(gours.cpu(), gref, TOL, f"{cls}/{scheme}/{acc} bwd")
+    for cls, scheme, acc in [("diffusion1D", "Central", 6), ("diffusion1D", "Central_4th", 4), ("dudx_1D", "Upwind", 3)]:
+        x = u1d.clone().requires_grad_(True)
+        y = O.stencil1d(x, scheme, acc)
+        cot = torch.randn(y.shape, generator=gen)
+        (gref,) = torch.autograd.grad(y, x, cot)
+        xc = u1d.cuda().requires_grad_(True)
+        yc = _make_op(pk["ops"], cls, scheme, acc)(xc)
+        (gours,) = torch.autograd.grad(yc, xc, cot.cuda())
+        assert_parity(gours.cpu(), gref, TOL, f"{cls}/{scheme}/{acc} bwd")
+
+
+def test_operator_large_and_ragged_shapes(pk):
+    """Sizes that do not divide the kernels' tiles (kRows = 8, kVec = 4, 128 threads)."""
+    gen = torch.Generator().manual_seed(8)
+    for (b, h, w) in [(1, 7, 5), (2, 263, 257), (1, 130, 1031), (5, 9, 9)]:
+        u = torch.randn(b, 1, h, w, generator=gen) - 0.1
+        for cls, scheme, acc, axis in [("d2udx2_2D", "Central2", 6, 2), ("d2udy2_2D", "Central2", 2, 3),
+                                       ("dudx_2D", "Upwind1", 3, 2), ("dudy_2D", "Upwind1", 1, 3)]:
+            ref = O.stencil2d(u, scheme, acc, axis)
+            ours = _make_op(pk["ops"], cls, scheme, acc)(u.cuda())
+            assert_parity(ours.cpu(), ref, TOL, f"{cls} {b}x{h}x{w}")
+
+
+def test_operator_api_errors(pk):
+    ops = pk["ops"]
+    with pytest.raises(AssertionError):
+        ops.d2udx2_2D("Central2", 3)
+    with pytest.raises(AssertionError):
+        ops.d2udy2_2D("Upwind1", 2)
+    with pytest.raises(AssertionError):
+        ops.diffusion1D("Forward", 2)
+    with pytest.raises(RuntimeError):
+        ops.dudx_2D()(torch.zeros(1, 1, 8, 8))             # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        ops.advection1d()(torch.zeros(1, 1, 8).cuda())
+    assert ops.dudx_2D().accuracy == 1 and ops.dudx_2D().xscheme == "Upwind1"
+    assert ops.d2udx2_2D().accuracy == 2
+
+
+def test_rhs_all_names_fused_and_composed(pk):
+    g = load_golden("rhs.npz")
+    ops, rhs = pk["ops"], pk["rhs"]
+    u1, v1, mu = g["u1"].cuda(), g["v1"].cuda(), g["mu"].cuda()
+    names = [str(s) for s in g["names"]]
+    for aa, da in ((1, 2), (3, 6)):
+        dudx, dudy = ops.dudx_2D(accuracy=aa), ops.dudy_2D(accuracy=aa)
+        d2x, d2y = ops.d2udx2_2D(accuracy=da), ops.d2udy2_2D(accuracy=da)
+        for name in names:
+            fld = v1 if name.endswith("v") else u1
+            ax, ay = O.wrap_x(fld, aa), O.wrap_y(fld, aa)
+            f = getattr(rhs, name)
+            ours = f(u1, v1, mu, dudx, dudy, d2x, d2y, ax, ay, 0.1, 0.08, 0.1 ** 2, 0.08 ** 2)
+            assert_parity(ours.cpu(), g[f"{name}/{aa}{da}"], TOL, f"{name}/{aa}{da} fused")
+            # composed path: wrap one operator in a lambda so the fused plan is refused
+            ours2 = f(u1, v1, mu, lambda t: dudx(t), dudy, lambda t: d2x(t), d2y, ax, ay,
+                      0.1, 0.08, 0.1 ** 2, 0.08 ** 2)
+            assert_parity(ours2.cpu(), g[f"{name}/{aa}{da}"], TOL, f"{name}/{aa}{da} composed")
+    w = g["ks_w"].cuda()
+    ours = rhs.ks1d(torch.cat((w[:, :, -2:], w, w[:, :, :2]), 2), None, ops.dudx_1D("Upwind", 1),
+                    ops.diffusion1D("Central", 2), ops.diffusion1D("Central_4th", 2),
+                    torch.cat((w[:, :, -1:], w, w[:, :, :1]), 2), 0.3, 0.09, 0.0081)
+    assert_parity(ours.cpu(), g["ks1d"], TOL, "ks1d")
+
+
+def test_rhs_fused_gradients(pk):
+    ops, rhs = pk["ops"], pk["rhs"]
+    gen = torch.Generator().manual_seed(11)
+    n = 10
+    u1 = torch.randn(2, 1, n, n, generator=gen)
+    v1 = torch.randn(2, 1, n, n, generator=gen)
+    mu = torch.tensor([0.03, 0.06]).reshape(-1, 1, 1, 1)
+    cot = torch.randn(2, 1, n, n, generator=gen)
+    o = O.Ops(1, 2)
+    dudx, dudy = ops.dudx_2D(accuracy=1), ops.dudy_2D(accuracy=1)
+    d2x, d2y = ops.d2udx2_2D(accuracy=2), ops.d2udy2_2D(accuracy=2)
+    for name in ("burgers2DFu", "burgers2DFv", "rdFu", "rdFv", "burgers2Dpv", "convecu"):
+        leaves = [t.clone().requires_grad_(True) for t in (u1, v1, mu)]
+        fld = leaves[1] if name.endswith("v") else leaves[0]
+        y = O.rhs(name, leaves[0], leaves[1], leaves[2], o, O.wrap_x(fld), O.wrap_y(fld), 0.1, 0.08, 0.01, 0.0064)
+        gref = torch.autograd.grad(y, leaves, cot, allow_unused=True)
+        lc = [t.cuda().requires_grad_(True) for t in (u1, v1, mu)]
+        fc = lc[1] if name.endswith("v") else lc[0]
+        yc = getattr(rhs, name)(lc[0], lc[1], lc[2], dudx, dudy, d2x, d2y, O.wrap_x(fc), O.wrap_y(fc),
+                                0.1, 0.08, 0.01, 0.0064)
+        gours = torch.autograd.grad(yc, lc, cot.cuda(), allow_unused=True)
+        for a, b, what in zip(gours, gref, ("u1", "v1", "mu")):
+            if b is None:
+                assert a is None or a.abs().max() == 0
+                continue
+            assert_parity(a.cpu(), b, 2e-5, f"{name} grad_{what}")
+
+
+def test_mesh_converter_against_reference_golden(pk):
+    g = load_golden("mesh.npz")
+    M = pk["mesh"]
+    for c in (33, 49):
+        m = M(257, c, dim=2)
+        d = m.down(g["f257"].cuda())
+        assert_parity(d.cpu(), g[f"down/257/{c}"], TOL, f"down 257->{c}")
+        assert_parity(m.up(d).cpu(), g[f"up/{c}/257"], TOL, f"up {c}->257")
+    for c in (17, 13, 9):
+        m = M(65, c, dim=2)
+        d = m.down(g["r65"].cuda())
+        assert_parity(d.cpu(), g[f"down/65/{c}"], TOL, f"down 65->{c}")
+        assert_parity(m.up(d).cpu(), g[f"up/{c}/65"], TOL, f"up {c}->65")
+    m = M((40, 57), (9, 13), dim=2)
+    assert_parity(m.down(g["rect"].cuda()).cpu(), g["rect_down"], TOL, "rect down")
+    assert_parity(m.up(g["rect"].cuda()).cpu(), g["rect_up"], TOL, "rect up")
+    for ac in (1, 0):
+        m = M(31, 7, dim=2, align_corners=bool(ac))
+        d = m.down(g[f"ac{ac}_in"].cuda())
+        assert_parity(d.cpu(), g[f"ac{ac}_down"], TOL, f"ac{ac} down")
+        assert_parity(m.up(d).cpu(), g[f"ac{ac}_up"], TOL, f"ac{ac} up")
+    m1 = M(101, 11, dim=1)
+    d = m1.down(g["line"].cuda())
+    assert_parity(d.cpu(), g["line_down"], TOL, "1-D down")
+    assert_parity(m1.up(d).cpu(), g["line_up"], TOL, "1-D up")
+
+
+def test_mesh_converter_adjoint(pk):
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 2, 33, 33, generator=gen)
+    for (size, fn, mode) in ((9, "down", None), (65, "up", None)):
+        xr = x.clone().requires_grad_(True)
+        y = O.mesh_down(xr, size) if fn == "down" else O.mesh_up(xr, size)
+        cot = torch.randn(y.shape, generator=gen)
+        (gref,) = torch.autograd.grad(y, xr, cot)
+        xc = x.cuda().requires_grad_(True)
+        m = pk["mesh"](size if fn == "up" else 33, size if fn == "down" else 33, dim=2)
+        yc = getattr(m, fn)(xc)
+        (gours,) = torch.autograd.grad(yc, xc, cot.cuda())
+        assert_parity(gours.cpu(), gref, TOL, f"mesh {fn} adjoint")
+
+
+# --------------------------------------------------------------------- Tier B
+CASES = {
+    "burgers_p": dict(cmesh=33, rhsu="burgers2Dpu", rhsv="burgers2Dpv", dt=0.02, length=3.2, mu=0.07),
+    "rd_p": dict(cmesh=49, rhsu="rdpu", rhsv="rdpv", dt=0.002, length=6.4, mu=1.3),
+    "burgers_f": dict(cmesh=49, rhsu="burgers2DFu", rhsv="burgers2DFv", dt=0.02, length=3.2, mu=0.07),
+    "rd_f": dict(cmesh=49, rhsu="rdFu", rhsv="rdFv", dt=0.002, length=6.4, mu=1.3),
+}
+SMALL = {"burgers_p": 9, "rd_p": 13, "burgers_f": 13, "rd_f": 13}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_pde_du_full_size_against_reference_golden(pk, case):
+    g = load_golden("pde_du_257.npz")
+    c = CASES[case]
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    mu = torch.tensor([c["mu"]]).reshape(1, 1, 1, 1).cuda()
+    ours = step.pde_du(g["u257"].cuda(), mu)
+    assert_parity(ours.cpu(), g[f"{case}/257"], TOL, case)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_pde_du_small_grads_update_rollout_against_reference_golden(pk, case):
+    g = load_golden("pde_du_65.npz")
+    c = CASES[case]
+    step = pk["CoarseStep"](65, SMALL[case], c["rhsu"], c["rhsv"], c["dt"], float(g[f"{case}/length"]))
+    mu = g[f"{case}/mu"].cuda()
+    u = g["u65"].cuda().requires_grad_(True)
+    m = mu.clone().requires_grad_(True)
+    y = step.pde_du(u, m)
+    assert_parity(y.detach().cpu(), g[f"{case}/pdeu"], TOL, case + " pdeu")
+    gu, gm = torch.autograd.grad(y, (u, m), g["cot65"].cuda())
+    assert_parity(gu.cpu(), g[f"{case}/grad_u"], TOL, case + " grad_u")
+    if g[f"{case}/grad_mu"].abs().max() > 0:
+        assert_parity(gm.cpu(), g[f"{case}/grad_mu"], 2e-5, case + " grad_mu")
+    else:
+        assert gm.abs().max().item() == 0
+    upd = step.step_update(g["u65"].cuda(), mu, g["nn65"].cuda(), g["outmean"], g["outstd"])
+    assert_parity(upd.cpu(), g[f"{case}/update"], TOL, case + " update")
+    roll = step.pde_only_rollout(g["u65"].cuda(), mu, 5)[-1]
+    assert_parity(roll.cpu(), g[f"{case}/rollout5"], TOL, case + " rollout5")
+
+
+@pytest.mark.parametrize("case", ["burgers_p", "burgers_f", "rd_f"])
+def test_step_update_adjoint(pk, case):
+    """u_next = padBC_rd(nn*s+m) + u + pde_du(u): gradients to u, mu and nn."""
+    gen = torch.Generator().manual_seed(21)
+    c = CASES[case]
+    cm = SMALL[case]
+    length = c["length"] * (cm - 1) / (c["cmesh"] - 1) * 0.5
+    ostep = O.CoarseStep(65, cm, c["rhsu"], c["rhsv"], c["dt"], length)
+    step = pk["CoarseStep"](65, cm, c["rhsu"], c["rhsv"], c["dt"], length)
+    u = torch.randn(2, 2, 65, 65, generator=gen) * 0.5
+    nn = torch.randn(2, 2, 64, 64, generator=gen)
+    mu = torch.tensor([0.03, 0.06]).reshape(-1, 1, 1, 1)
+    om, os_ = torch.tensor([0.01, -0.02]).reshape(1, 2, 1, 1), torch.tensor([0.3, 0.2]).reshape(1, 2, 1, 1)
+    cot = torch.randn(2, 2, 65, 65, generator=gen)
+    lv = [t.clone().requires_grad_(True) for t in (u, mu, nn)]
+    yref = O.ppnn_update(lv[0], ostep.pde_du(lv[0], lv[1]), lv[2], om, os_)
+    gref = torch.autograd.grad(yref, lv, cot, allow_unused=True)
+    lc = [t.cuda().requires_grad_(True) for t in (u, mu, nn)]
+    y = step.step_update(lc[0], lc[1], lc[2], om, os_)
+    assert_parity(y.detach().cpu(), yref.detach(), TOL, "update fwd")
+    gours = torch.autograd.grad(y, lc, cot.cuda(), allow_unused=True)
+    assert_parity(gours[0].cpu(), gref[0], TOL, "update grad_u")
+    assert_parity(gours[2].cpu(), gref[2], TOL, "update grad_nn")
+    if gref[1] is not None and gref[1].abs().max() > 0:
+        assert_parity(gours[1].cpu(), gref[1], 2e-5, "update grad_mu")
+
+
+@pytest.mark.parametrize("case", ["burgers_p", "rd_p"])
+def test_step_inputs(pk, case):
+    gen = torch.Generator().manual_seed(22)
+    c = CASES[case]
+    ostep = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    g = load_golden("pde_du_257.npz")
+    u = torch.cat((g["u257"], g["u257"].flip(1) * 0.7), 0)
+    mu = torch.tensor([c["mu"], c["mu"] * 0.5]).reshape(-1, 1, 1, 1)
+    st = dict(inmean=torch.tensor([0.1, -0.2]).reshape(1, 2, 1, 1), instd=torch.tensor([0.9, 1.3]).reshape(1, 2, 1, 1),
+              pdemean=torch.tensor([1e-3, -2e-3]).reshape(1, 2, 1, 1), pdestd=torch.tensor([0.02, 0.05]).reshape(1, 2, 1, 1),
+              mumean=torch.tensor(0.04), mustd=torch.tensor(0.01))
+    pde = ostep.pde_du(u, mu)
+    a, _, cc = O.ppnn_net_inputs(u, mu, pde, st["inmean"], st["instd"], st["mumean"], st["mustd"],
+                                 st["pdemean"], st["pdestd"])
+    un, pn, pd = step.step_inputs(u.cuda(), mu.cuda(), st["inmean"], st["instd"], st["pdemean"], st["pdestd"],
+                                  want_pdeu=True)
+    assert_parity(un.cpu(), a, TOL, "u_norm")
+    # the normalised increment is O(1) while pdeu is O(1e-2): compare against the same scale
+    assert_parity(pn.cpu() * st["pdestd"], cc * st["pdestd"], TOL, "pdeu_norm")
+    assert_parity(pd.cpu(), pde, TOL, "pdeu")
+    un2, pn2, pd2 = step.step_inputs(u.cuda(), mu.cuda(), st["inmean"], st["instd"])
+    assert pn2 is None and pd2 is None
+    assert torch.equal(un2, un)
+
+
+def test_coarse_only_solver(pk):
+    gen = torch.Generator().manual_seed(23)
+    c = CASES["burgers_p"]
+    ostep = O.CoarseStep(49, 49, c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    step = pk["CoarseStep"](49, 49, c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    uc = O.append_endpoint(torch.randn(3, 2, 48, 48, generator=gen) * 0.4)
+    mu = torch.tensor([0.02, 0.04, 0.07]).reshape(-1, 1, 1, 1)
+    ref = ostep.coarse_only_increment(uc, mu)
+    assert_parity(step.coarse_increment(uc.cuda(), mu.cuda()).cpu(), ref, TOL, "coarse increment")
+    assert_parity(step.coarse_increment(uc.cuda(), mu.cuda(), add_state=True).cpu(), uc + ref, TOL, "coarse step")
+
+
+@pytest.mark.parametrize("mode", ["as_written", "intended"])
+def test_fine_solver_against_reference_golden(pk, mode):
+    g = load_golden("fine.npz")
+    fb = pk["FineBurgers"](mode=mode)
+    u, v, mu = g["u0"].cuda(), g["v0"].cuda(), g["mu"].cuda()
+    for i in range(4):
+        u, v = fb.step(u, v, mu)
+        if i in (0, 3):
+            assert_parity(u.cpu(), g[f"{mode}/u{i + 1}"], TOL, f"{mode} u{i + 1}")
+            assert_parity(v.cpu(), g[f"{mode}/v{i + 1}"], TOL, f"{mode} v{i + 1}")
+
+
+@pytest.mark.parametrize("n,endpoint,aa,da", [(257, True, 3, 6), (256, False, 3, 6), (100, True, 1, 2),
+                                               (131, False, 2, 4), (1025, True, 3, 6)])
+def test_fine_solver_sizes_and_accuracies(pk, n, endpoint, aa, da):
+    gen = torch.Generator().manual_seed(31)
+    b = 2
+    coef = torch.randn(b, 81, 2, generator=gen)
+    u = O.fourier_initial_condition(coef, n) - 0.5
+    v = O.fourier_initial_condition(torch.randn(b, 81, 2, generator=gen), n) - 0.6
+    mu = torch.tensor([0.025, 0.065]).reshape(-1, 1, 1, 1)
+    for mode in ("as_written", "intended"):
+        fb = pk["FineBurgers"](mode=mode, adv_accuracy=aa, diff_accuracy=da, endpoint=endpoint)
+        ur, vr = O.fine_burgers_step(u, v, mu, mode=mode, adv_accuracy=aa, diff_accuracy=da,
+                                     period_endpoint=endpoint)
+        uo, vo = fb.step(u.cuda(), v.cuda(), mu.cuda())
+        # one step moves the state by O(dt): compare the INCREMENT at 1e-5 as well as the state
+        assert_parity(uo.cpu(), ur, TOL, f"fine {n} {mode} u")
+        assert_parity(vo.cpu(), vr, TOL, f"fine {n} {mode} v")
+        assert_parity(uo.cpu() - u, ur - u, 2e-4, f"fine {n} {mode} du")
+        assert_parity(vo.cpu() - v, vr - v, 2e-4, f"fine {n} {mode} dv")
+
+
+def test_fine_solver_run_snapshots_and_graph(pk):
+    gen = torch.Generator().manual_seed(32)
+    n, b = 65, 3
+    u = O.fourier_initial_condition(torch.randn(b, 81, 2, generator=gen), n)
+    v = O.fourier_initial_condition(torch.randn(b, 81, 2, generator=gen), n) - 0.6
+    mu = torch.linspace(0.025, 0.065, b).reshape(-1, 1, 1, 1)
+    ur, vr, sur, svr = O.fine_burgers_run(u, v, mu, 25, every=6)
+    fb = pk["FineBurgers"]()
+    for graph in (False, True):
+        uo, vo, su, sv = fb.run(u.cuda(), v.cuda(), mu.cuda(), 25, every=6, graph=graph)
+        assert len(su) == len(sur) == 5
+        assert_parity(uo.cpu(), ur, TOL, f"run graph={graph} u")
+        assert_parity(vo.cpu(), vr, TOL, f"run graph={graph} v")
+        for k in range(len(su)):
+            assert_parity(su[k].cpu(), sur[k], TOL, f"snapshot {k} graph={graph}")
+            assert_parity(sv[k].cpu(), svr[k], TOL, f"snapshot v {k} graph={graph}")
+
+
+def test_rollout_drift_100_steps(pk):
+    """PDE-only rollout (test_predict_2Dp.py:116) over 100 steps vs the fp32 and the
+    fp64 oracle: the drift must stay at the reference's own fp32 noise floor."""
+    g = load_golden("pde_du_257.npz")
+    c = CASES["burgers_p"]
+    ostep = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    mu = torch.tensor([0.05]).reshape(1, 1, 1, 1)
+    u0 = g["u257"]
+    ref32 = O.pde_only_rollout(ostep, u0, mu, 100)
+    ref64 = O.pde_only_rollout(ostep, u0.double(), mu.double(), 100)
+    ours = step.pde_only_rollout(u0.cuda(), mu.cuda(), 100)
+    from conftest import rel_l2
+    d_ours = [rel_l2(ours[k].cpu(), ref64[k]) for k in (0, 9, 49, 99)]
+    d_ref = [rel_l2(ref32[k], ref64[k]) for k in (0, 9, 49, 99)]
+    print("drift vs fp64 (ours):", d_ours, " (reference fp32):", d_ref)
+    for k in (0, 9, 49, 99):
+        assert_parity(ours[k].cpu(), ref32[k], 1e-4 if k else TOL, f"rollout step {k + 1}")
+    assert d_ours[-1] < 1e-4
+
+
+def test_batch_independence_and_linearity_at_scale(pk):
+    """Size-independent properties at a batch the oracle cannot afford:
+    (i) every sample of a large batch equals the same sample run alone;
+    (ii) the RD 'p' step is linear in the state (pure scaled Laplacian)."""
+    gen = torch.Generator(device="cuda").manual_seed(41)
+    step = pk["CoarseStep"](257, 49, "rdpu", "rdpv", 0.002, 6.4)
+    B = 300
+    u = torch.randn(B, 2, 257, 257, device="cuda", generator=gen)
+    mu = torch.linspace(0.2, 1.3, B, device="cuda").reshape(-1, 1, 1, 1)
+    y = step.pde_du(u, mu)
+    for k in (0, 149, 299):
+        assert torch.equal(step.pde_du(u[k:k + 1].clone(), mu[k:k + 1]), y[k:k + 1])
+    a, b = 0.37, -1.9
+    y2 = step.pde_du(a * u + b * u.flip(0), mu)
+    lin = a * y + b * step.pde_du(u.flip(0), mu)
+    assert_parity(y2.cpu(), lin.cpu(), 2e-5, "linearity")
+    bstep = pk["CoarseStep"](257, 33, "burgers2Dpu", "burgers2Dpv", 0.02, 3.2)
+    yb = bstep.step_update(u, mu * 0.05)
+    assert torch.equal(bstep.step_update(u[7:8].clone(), mu[7:8] * 0.05), yb[7:8])
+
+
+def test_no_cpu_fallback(pk):
+    step = pk["CoarseStep"](65, 9, "burgers2Dpu", "burgers2Dpv", 0.02, 3.2)
+    with pytest.raises(RuntimeError):
+        step.pde_du(torch.zeros(1, 2, 65, 65), torch.zeros(1, 1, 1, 1))
+    with pytest.raises(RuntimeError):
+        pk["mesh"](65, 9, dim=2).down(torch.zeros(1, 1, 65, 65))
+    with pytest.raises(RuntimeError):
+        pk["FineBurgers"]().step(torch.zeros(1, 1, 33, 33), torch.zeros(1, 1, 33, 33), torch.zeros(1))

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the fused PDE-preserving step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+Workload (BASELINE.json configs[1], cases/RD_pPDE.yaml): one "step" is ONE launch
+of the fused coarse-grid step kernel over a batch of B samples per GPU
+
+    u_next = padBC_rd(nn_out*outstd + outmean) + u + pde_du(u, mu)      (train2D.py:235-238)
+
+with F = 257, C = 49, rhs = rdpu/rdpv, dt = 0.002, length = 6.4, mu = linspace(.2,1.3,12)
+repeated, synthetic periodic fields (Fourier fields of operators.py:436-443, shifted to
+mixed sign) and a random stand-in for the network output.  Unit: point-updates/s, one
+point-update = one fp32 value of one field advanced one step.
+
+* value      -- inputs resident in HBM, CUDA-event timed, max over ranks.
+* e2e        -- the same step through the public API with HOST (pinned) buffers:
+                H2D of u and nn_out, kernel, D2H of u_next, inside the timed region.
+* roofline   -- HBM bound: 12 B per point-update (read u, read nn_out, write u_next)
+                / measured launch time, against MEASURED_PEAKS.json.
+* cpu_baseline -- the CPU oracle (oracle/ppnn_oracle.py, the reference's ATen op
+                sequence) on a bounded sample of the same workload on this host's cores.
+Multi-GPU: samples are independent, so ranks own disjoint shards of the batch and there
+is no data-path collective (weak scaling: B per GPU fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CASE = dict(fine=257, coarse=49, rhsu="rdpu", rhsv="rdpv", dt=0.002, length=6.4,
+            paralow=0.2, parahigh=1.3, num_para=12)
+B_PER_GPU = 1920            # 12 mu x 16 ICs x 10 time levels: 1/10 of the train2D.py:121 precompute batch
+BYTES_PER_POINT = 12        # read u + read nn_out + write u_next
+METRIC = "fused_pde_step_point_updates_per_s"
+UNIT = "Gpoint-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="samples per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel timings")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-batch", type=int, default=240)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- inputs
+def synth_fields(B, F, device, seed):
+    """Smooth periodic [B,2,F,F] state: random 81-mode Fourier sums like the reference
+    generator (operators.py:436-443), min-max normalised and shifted to mixed sign."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.linspace(0, 2 * torch.pi, F, device=device)
+    kk = torch.arange(-4, 5, device=device, dtype=torch.float32)
+    sx, cx = torch.sin(kk[:, None] * x[None]), torch.cos(kk[:, None] * x[None])      # [9,F]
+    out = torch.empty(B, 2, F, F, device=device)
+    chunk = 64
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        a = torch.randn(nb * 2, 9, 9, device=device, generator=g)
+        c = torch.randn(nb * 2, 9, 9, device=device, generator=g)
+        # sum_kl a_kl sin(kx+ly) + c_kl cos(kx+ly), expanded with the angle-sum identities
+        f = (torch.einsum("nkl,ki,lj->nij", a, sx, cx) + torch.einsum("nkl,ki,lj->nij", a, cx, sx)
+             + torch.einsum("nkl,ki,lj->nij", c, cx, cx) - torch.einsum("nkl,ki,lj->nij", c, sx, sx))
+        lo = f.amin(dim=(1, 2), keepdim=True)
+        hi = f.amax(dim=(1, 2), keepdim=True)
+        out[b0:b0 + nb] = ((f - lo) / (hi - lo) + 0.1 - 0.6).reshape(nb, 2, F, F)
+    return out
+
+
+def make_mu(B, device, offset=0):
+    import torch
+    base = torch.linspace(CASE["paralow"], CASE["parahigh"], CASE["num_para"], device=device)
+    idx = (torch.arange(B, device=device) + offset) % CASE["num_para"]
+    return base[idx].reshape(B, 1, 1, 1).contiguous()
+
+
+STATS = dict(outmean=[1.0e-4, -2.0e-4], outstd=[3.0e-3, 2.0e-3])
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = []
+        for line in open(self.tmp.name):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == 7 and parts[0].isdigit():
+                rows.append(parts)
+        os.unlink(self.tmp.name)
+        if not rows:
+            return out
+        busy = [r for r in rows if r[2].isdigit() and int(r[2]) > 0] or rows
+        clk = sorted(int(r[0]) for r in busy)
+        out["sm_mhz"] = clk[len(clk) // 2]
+        out["sm_max_mhz"] = int(rows[0][1])
+        out["samples"] = len(busy)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        out["reasons"] = [n for k, n in enumerate(names) if any(r[3 + k] == "Active" for r in busy)]
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_oracle_step_fn(B):
+    """Bounded sample of the workload on the host cores, through the oracle port."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ppnn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    F = CASE["fine"]
+    u = synth_fields(B, F, torch.device("cpu"), 10)
+    mu = make_mu(B, torch.device("cpu"))
+    nn = torch.randn(B, 2, F - 1, F - 1, generator=torch.Generator().manual_seed(11))
+    om = torch.tensor(STATS["outmean"]).reshape(1, 2, 1, 1)
+    os_ = torch.tensor(STATS["outstd"]).reshape(1, 2, 1, 1)
+    step = O.CoarseStep(F, CASE["coarse"], CASE["rhsu"], CASE["rhsv"], CASE["dt"], CASE["length"])
+
+    def run():
+        with torch.no_grad():
+            return O.ppnn_update(u, step.pde_du(u, mu), nn, om, os_)
+    return run, B * 2 * F * F
+
+
+def time_cpu(B, min_seconds=10.0, max_reps=20):
+    run, pts = cpu_oracle_step_fn(B)
+    run()                                                   # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < max_reps and (time.perf_counter() - t0 < min_seconds or reps < 2):
+        run()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return pts / dt / 1e9, reps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    B = args.cpu_batch
+    run, pts = cpu_oracle_step_fn(B)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = pts / dt / 1e9
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, 1, sample_of=args.batch),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{B} of {args.batch} samples per step, oracle/ppnn_oracle.py (the reference's "
+                                       f"ATen op sequence: interpolate/conv2d/cat) on {cores} torch threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n, sample_of=None):
+    c = {"workload": "cases/RD_pPDE.yaml fused step: u_next = padBC_rd(nn*outstd+outmean) + u + pde_du(u,mu)",
+         "fine": CASE["fine"], "coarse": CASE["coarse"], "rhs": [CASE["rhsu"], CASE["rhsv"]],
+         "dt": CASE["dt"], "length": CASE["length"], "batch_per_gpu": B, "global_batch": B * n,
+         "parallelism": f"batch-sharded x{n}, no data-path collective",
+         "l2": "inputs (3.0 GB per GPU) exceed the 126 MB L2; no flush needed"}
+    if sample_of:
+        c["sample_of_batch"] = sample_of
+    return c
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ppnn_b200 import CoarseStep, FineBurgers, _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    F, B = CASE["fine"], args.batch
+    step = CoarseStep(F, CASE["coarse"], CASE["rhsu"], CASE["rhsv"], CASE["dt"], CASE["length"])
+    u = synth_fields(B, F, dev, 10 + rank)
+    mu = make_mu(B, dev, offset=rank * B)
+    muv = mu.reshape(-1).contiguous()
+    nn = torch.randn(B, 2, F - 1, F - 1, device=dev, generator=torch.Generator(device=dev).manual_seed(11 + rank))
+    out = torch.empty_like(u)
+    om, os_ = L.f2(STATS["outmean"]), L.f2(STATS["outstd"])
+    pts = B * 2 * F * F
+
+    def kernel_step():
+        step.step_update_(u, muv, nn, om, os_, out)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- value: resident inputs, one launch per step ---------------------------------
+    ms = timed(kernel_step, args.steps, max(args.warmup, 3))
+    value = world * pts / (ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers, H2D + kernel + D2H per step, chunked over two streams -----
+    nchunk = 8
+    cb = (B + nchunk - 1) // nchunk
+    u_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True).copy_(u)
+    nn_h = torch.empty(nn.shape, dtype=torch.float32, pin_memory=True).copy_(nn)
+    out_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    dbuf = [(torch.empty((cb,) + tuple(u.shape[1:]), device=dev), torch.empty((cb,) + tuple(nn.shape[1:]), device=dev),
+             torch.empty((cb,) + tuple(u.shape[1:]), device=dev)) for _ in streams]
+
+    def e2e_step():
+        cur = torch.cuda.current_stream()
+        for s in streams:
+            s.wait_stream(cur)
+        for c in range(nchunk):
+            b0, b1 = c * cb, min((c + 1) * cb, B)
+            if b0 >= b1:
+                break
+            s = streams[c % 2]
+            du, dn, do = dbuf[c % 2]
+            with torch.cuda.stream(s):
+                du[:b1 - b0].copy_(u_h[b0:b1], non_blocking=True)
+                dn[:b1 - b0].copy_(nn_h[b0:b1], non_blocking=True)
+                step.step_update_(du[:b1 - b0], muv[b0:b1], dn[:b1 - b0], om, os_, do[:b1 - b0])
+                out_h[b0:b1].copy_(do[:b1 - b0], non_blocking=True)
+        for s in streams:
+            cur.wait_stream(s)
+
+    e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e = timed(e2e_step, e2e_steps, 1)
+    e2e_value = world * pts / (ms_e2e * 1e-3) / 1e9
+    torch.cuda.synchronize()
+    e2e_ok = bool(torch.equal(out_h[:4], out[:4].cpu()))
+    h2d = (u.numel() + nn.numel()) * 4
+    d2h = u.numel() * 4
+
+    # ---- secondary kernels (same case), device resident ------------------------------
+    extras = {}
+    if not args.no_extras:
+        reps = max(3, min(args.steps, 10))
+        stats = dict(inmean=L.f2([0.0, 0.0]), instd=L.f2([0.3, 0.3]), pdemean=L.f2([0.0, 0.0]), pdestd=L.f2([1e-3, 1e-3]))
+        t = timed(lambda: step.step_inputs(u, muv, stats["inmean"], stats["instd"], stats["pdemean"], stats["pdestd"]), reps, 2)
+        extras["step_inputs_K1"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 12,
+                                    "hbm_gbs": 12 * pts / t / 1e6}
+        t = timed(lambda: step.step_update_(u, muv, None, None, None, out), reps, 2)
+        extras["pde_only_update"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
+        lib = L.load()
+        import ctypes as C
+        gu = torch.empty_like(u)
+        gmu = torch.empty(B, device=dev)
+
+        def adj():
+            L.check(lib.ppnn_pde_du_bwd(C.byref(step.cfg), u.data_ptr(), muv.data_ptr(), out.data_ptr(), gu.data_ptr(),
+                                        gmu.data_ptr(), B, 1, L.stream()), "bwd")
+        t = timed(adj, reps, 2)
+        extras["step_adjoint"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
+        del gu, u_h, nn_h, out_h, dbuf
+        # datagen (BASELINE config 4): fused Burgers step, 64 samples x 1025^2 per GPU
+        fb = FineBurgers()
+        n, bf = 1025, 64
+        fu = synth_fields(bf, n, dev, 99)            # [bf,2,n,n]
+        a, b_ = fu[:, 0].contiguous(), fu[:, 1].contiguous()
+        a2, b2 = torch.empty_like(a), torch.empty_like(b_)
+        mf = make_mu(bf, dev).reshape(-1) * 0.05
+        fpts = bf * 2 * n * n
+        t = timed(lambda: fb.step_(a, b_, mf, a2, b2), reps * 2, 3)
+        extras["fine_burgers_step_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
+                                               "hbm_gbs": 8 * fpts / t / 1e6}
+        fbi = FineBurgers(mode="intended")
+        t = timed(lambda: fbi.step_(a, b_, mf, a2, b2), reps * 2, 3)
+        extras["fine_burgers_step_intended_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
+                                                        "hbm_gbs": 8 * fpts / t / 1e6}
+
+    clocks = sampler.stop() if sampler else None
+
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak = 6650.0
+    achieved = BYTES_PER_POINT * pts / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("coarse_step_update_bytes_per_launch")
+    except Exception:
+        pass
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e, "steps": e2e_steps, "matches_resident_result": e2e_ok,
+                    "api": "ppnn_b200.CoarseStep.step_update_ -> ppnn_step_update (C ABI), pinned host buffers, "
+                           "8 chunks over 2 streams"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "coarse_step_kernel<MODE_UPDATE>",
+                         "algorithmic_bytes_per_launch": BYTES_PER_POINT * pts,
+                         "bytes_per_point_update": BYTES_PER_POINT},
+            "extras": extras}
+    if world == 1 and not args.no_cpu:
+        v, reps, dt = time_cpu(args.cpu_batch)
+        import torch as _t
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_batch} of {B} samples x {reps} reps ({dt:.2f} s each), "
+                                          "oracle/ppnn_oracle.py (reference ATen op sequence) on all host threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

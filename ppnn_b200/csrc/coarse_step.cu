@@ -33,10 +33,10 @@ struct StepIO {
     float m1[2], s1[2];    // pdemean/pdestd (INPUTS)
 };
 
-constexpr int kRowUnroll = 4;
+constexpr int kRowUnroll = 8;
 
 template <int MODE>
-__global__ void __launch_bounds__(576)
+__global__ void __launch_bounds__(512, 2)
 coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
     extern __shared__ float smem[];
     const int nn2 = p.NH * p.NW;
@@ -82,76 +82,130 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
     const int nband = (p.FH + band_rows - 1) / band_rows;
     const int nstrip = 2 * nband * nchunk;
     const int PH = p.FH - 1, PW = p.FW - 1;                    // network grid (no endpoint)
+    const size_t nplane = (size_t)PH * PW;
 
     for (int s = warp; s < nstrip; s += nwarp) {
         // consecutive warps take consecutive column chunks of the same band
-        int chunk = s % nchunk;
-        int t2 = s / nchunk;
-        int f = t2 % 2;
-        int band = t2 / 2;
-        int j = chunk * 32 + lane;
-        bool active = j < p.FW;
-        int jc = active ? j : p.FW - 1;
+        const int chunk = s % nchunk;
+        const int t2 = s / nchunk;
+        const int f = t2 & 1;
+        const int band = t2 >> 1;
+        const int j = chunk * 32 + lane;
+        const bool active = j < p.FW;
+        const int jc = active ? j : p.FW - 1;
         const float* rf = f ? rv : ru;
 
         float wy[4]; int j0;
         cubic_entry(p.suw, jc, &j0, wy);
-        int cj0 = ext_index(j0 - 1, p.CW), cj1 = ext_index(j0, p.CW),
-            cj2 = ext_index(j0 + 1, p.CW), cj3 = ext_index(j0 + 2, p.CW);
+        const float* rc0 = rf + ext_index(j0 - 1, p.CW);
+        const float* rc1 = rf + ext_index(j0, p.CW);
+        const float* rc2 = rf + ext_index(j0 + 1, p.CW);
+        const float* rc3 = rf + ext_index(j0 + 2, p.CW);
         auto yrow = [&](int I) -> float {     // W-pass of row I of the extended coarse increment
-            const float* r = rf + ext_index(I, p.CH) * p.NW;
-            return r[cj0] * wy[0] + r[cj1] * wy[1] + r[cj2] * wy[2] + r[cj3] * wy[3];
+            const int o = ext_index(I, p.CH) * p.NW;
+            return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
         };
 
-        int r0 = band * band_rows;
-        int r1 = min(r0 + band_rows, p.FH);
+        const int r0 = band * band_rows;
+        const int r1 = min(r0 + band_rows, p.FH);
         int base = rowi[r0];
         float h0 = yrow(base - 1), h1 = yrow(base), h2 = yrow(base + 1), h3 = yrow(base + 2);
-
-        const float* up = ub + f * plane + jc;
-        float* op = io.out ? io.out + ((size_t)b * 2 + f) * plane + jc : nullptr;
-        const size_t nplane = (size_t)PH * PW;
-        const int jn = jc == PW ? 0 : jc;                      // padBC_rd column fold
-        const float* np = (MODE == MODE_UPDATE && io.nn) ? io.nn + ((size_t)b * 2 + f) * nplane + jn : nullptr;
-        float* unp = (MODE == MODE_INPUTS) ? io.u_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
-        float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
-        const float m0 = io.m0[f], s0 = io.s0[f], m1 = io.m1[f], s1 = io.s1[f];
-
-        for (int i = r0; i < r1; i += kRowUnroll) {
-            float uu[kRowUnroll], nv[kRowUnroll];
-#pragma unroll
-            for (int q = 0; q < kRowUnroll; ++q) {
-                int ii = i + q;
-                bool ok = active && ii < r1;
-                if (MODE != MODE_PDEU) uu[q] = ok ? ld_stream(up + (size_t)ii * p.FW) : 0.f;
-                if (MODE == MODE_UPDATE)
-                    nv[q] = (ok && np) ? ld_stream(np + (size_t)(ii == PH ? 0 : ii) * PW) : 0.f;
+        // H-pass of fine row ii (advances the window when floor(ii*suh) moves on; warp-uniform)
+        auto prolong = [&](int ii) -> float {
+            const int i0 = rowi[ii];
+            const float4 wx = roww[ii];
+            if (i0 != base) {
+                if (i0 == base + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = yrow(i0 + 2); }
+                else { h0 = yrow(i0 - 1); h1 = yrow(i0); h2 = yrow(i0 + 1); h3 = yrow(i0 + 2); }
+                base = i0;
             }
+            return h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w;
+        };
+
+        const float m0 = f ? io.m0[1] : io.m0[0], s0 = f ? io.s0[1] : io.s0[0];
+        const float m1 = f ? io.m1[1] : io.m1[0], s1 = f ? io.s1[1] : io.s1[0];
+        const size_t off = ((size_t)b * 2 + f) * plane + (size_t)r0 * p.FW + jc;
+        const float* up = io.u + off;                          // row pointers, bumped by one pitch per row
+        float* op = io.out ? io.out + off : nullptr;
+
+        if (MODE == MODE_PDEU) {
+            for (int ii = r0; ii < r1; ++ii, op += p.FW) {
+                float pde = prolong(ii);
+                if (active) st_stream(op, pde);
+            }
+        } else if (MODE == MODE_UPDATE) {
+            const bool has_nn = io.nn != nullptr;
+            const int jn = jc == PW ? 0 : jc;                  // padBC_rd column fold
+            const float* nbase = has_nn ? io.nn + ((size_t)b * 2 + f) * nplane + jn : nullptr;
+            const float* np = has_nn ? nbase + (size_t)r0 * PW : nullptr;
+            const int rmain = min(r1, PH);                     // rows whose network row is the row itself
+            int ii = r0;
+            for (; ii + kRowUnroll <= rmain; ii += kRowUnroll) {
+                float uu[kRowUnroll], nv[kRowUnroll];
+                if (active) {
 #pragma unroll
-            for (int q = 0; q < kRowUnroll; ++q) {
-                int ii = i + q;
-                if (ii >= r1) break;                            // warp-uniform
-                int i0 = rowi[ii];
-                if (i0 != base) {                               // warp-uniform window advance
-                    if (i0 == base + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = yrow(i0 + 2); }
-                    else { h0 = yrow(i0 - 1); h1 = yrow(i0); h2 = yrow(i0 + 1); h3 = yrow(i0 + 2); }
-                    base = i0;
-                }
-                float4 wx = roww[ii];
-                float pde = h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w;
-                if (!active) continue;
-                if (MODE == MODE_PDEU) {
-                    st_stream(op + (size_t)ii * p.FW, pde);
-                } else if (MODE == MODE_UPDATE) {
-                    float v = np ? (nv[q] * s0 + m0) + uu[q] + pde : uu[q] + pde;
-                    st_stream(op + (size_t)ii * p.FW, v);
-                } else {
-                    if (op) st_stream(op + (size_t)ii * p.FW, pde);
-                    if (ii < PH && jc < PW) {
-                        st_stream(unp + (size_t)ii * PW, (uu[q] - m0) / s0);
-                        if (pnp) st_stream(pnp + (size_t)ii * PW, (pde - m1) / s1);
+                    for (int q = 0; q < kRowUnroll; ++q) uu[q] = ld_stream(up + (size_t)q * p.FW);
+                    if (has_nn) {
+#pragma unroll
+                        for (int q = 0; q < kRowUnroll; ++q) nv[q] = ld_stream(np + (size_t)q * PW);
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < kRowUnroll; ++q) {
+                    float pde = prolong(ii + q);
+                    if (active) {
+                        float v = has_nn ? (nv[q] * s0 + m0) + uu[q] + pde : uu[q] + pde;
+                        st_stream(op + (size_t)q * p.FW, v);
+                    }
+                }
+                up += (size_t)kRowUnroll * p.FW; op += (size_t)kRowUnroll * p.FW;
+                if (has_nn) np += (size_t)kRowUnroll * PW;
+            }
+            for (; ii < r1; ++ii, up += p.FW, op += p.FW) {    // ragged tail and the endpoint row
+                float pde = prolong(ii);
+                if (active) {
+                    float uu = ld_stream(up);
+                    float v = uu + pde;
+                    if (has_nn) v = (ld_stream(nbase + (size_t)(ii == PH ? 0 : ii) * PW) * s0 + m0) + uu + pde;
+                    st_stream(op, v);
+                }
+            }
+        } else {   // MODE_INPUTS
+            const float rs0 = 1.f / s0, rs1 = 1.f / s1;
+            const bool colok = active && jc < PW;
+            float* unp = io.u_norm + ((size_t)b * 2 + f) * nplane + (size_t)r0 * PW + jc;
+            float* pnp = io.p_norm ? io.p_norm + ((size_t)b * 2 + f) * nplane + (size_t)r0 * PW + jc : nullptr;
+            const int rmain = min(r1, PH);
+            int ii = r0;
+            for (; ii + kRowUnroll <= rmain; ii += kRowUnroll) {
+                float uu[kRowUnroll];
+                if (colok) {
+#pragma unroll
+                    for (int q = 0; q < kRowUnroll; ++q) uu[q] = ld_stream(up + (size_t)q * p.FW);
+                }
+#pragma unroll
+                for (int q = 0; q < kRowUnroll; ++q) {
+                    float pde = prolong(ii + q);
+                    if (op && active) st_stream(op + (size_t)q * p.FW, pde);
+                    if (colok) {
+                        st_stream(unp + (size_t)q * PW, div_by(uu[q] - m0, s0, rs0));
+                        if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
+                    }
+                }
+                up += (size_t)kRowUnroll * p.FW; unp += (size_t)kRowUnroll * PW;
+                if (op) op += (size_t)kRowUnroll * p.FW;
+                if (pnp) pnp += (size_t)kRowUnroll * PW;
+            }
+            for (; ii < r1; ++ii) {
+                float pde = prolong(ii);
+                if (op && active) st_stream(op, pde);
+                if (colok && ii < PH) {
+                    st_stream(unp, div_by(ld_stream(up) - m0, s0, rs0));
+                    if (pnp) st_stream(pnp, div_by(pde - m1, s1, rs1));
+                }
+                up += p.FW; unp += PW;
+                if (op) op += p.FW;
+                if (pnp) pnp += PW;
             }
         }
     }
@@ -210,7 +264,7 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     int band_rows = (p.FH + nband - 1) / nband;
     band_rows = (band_rows + kRowUnroll - 1) / kRowUnroll * kRowUnroll;
     int nstrip = 2 * nchunk * ((p.FH + band_rows - 1) / band_rows);
-    int warps = nstrip < 18 ? nstrip : 18;
+    int warps = nstrip < 16 ? nstrip : 16;
     if (warps < 4) warps = 4;
     kern<<<B, warps * 32, smem, (cudaStream_t)stream>>>(p, io, band_rows);
     return launch_status();

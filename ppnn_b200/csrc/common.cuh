@@ -125,6 +125,15 @@ __device__ __forceinline__ float add_reaction(float acc, int react, float u1, fl
     }
 }
 
+// x / s for a divisor whose reciprocal r = 1/s is already known: one multiply and
+// one Newton correction give the correctly rounded quotient (the IEEE division the
+// reference performs) without the slow-path division sequence.
+__device__ __forceinline__ float div_by(float x, float s, float r) {
+    float q = x * r;
+    float rem = fmaf(-q, s, x);
+    return fmaf(rem, r, q);
+}
+
 // streaming (read-once / write-once) global accesses: keep them out of L1
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void  st_stream(float* p, float v) { __stcs(p, v); }

@@ -1,0 +1,136 @@
+"""Dataset generation: the fine-grid explicit Burgers solver of the reference's
+``src/operators.py`` ``__main__`` block (lines 403-492), sharded by sample across
+GPUs with no communication.
+
+    torchrun --nproc-per-node 8 -m ppnn_b200.datagen --out burgers.pt --mesh 1025 \
+        --para 8 --repeat 64 --steps 20001 --every 200
+
+Per rank: samples ``shard_bounds(P, rank, world)``; initial conditions from per-sample
+RNG streams keyed by the GLOBAL sample index (the union over ranks equals the
+1-GPU run bit for bit); one fused kernel per time step replayed from a CUDA graph
+of ``every`` steps; snapshots are staged on the device and copied to pinned host
+memory on a side stream while the solver keeps running.  Output is the reference's
+wire format ``{'u': float32 [P, T, 2, F, F]}`` (what train2D.py:86 loads), one file
+per rank (``dist.shard_file``) unless ``--gather``.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import dist as D
+from .fused import FineBurgers
+
+
+def fourier_initial_condition(coef: torch.Tensor, n: int, device) -> torch.Tensor:
+    """Random 81-mode periodic field, min-max normalised to [0.1, 1.1]
+    (operators.py:423-445).  ``coef`` [B, (2m+1)^2, 2] holds the (sin, cos) N(0,1)
+    coefficients in the reference's (k, l) loop order; x = linspace(0, 2*pi, n)
+    includes the duplicated endpoint."""
+    B, m2, _ = coef.shape
+    modes = (int(round(math.sqrt(m2))) - 1) // 2
+    x = torch.linspace(0, 2 * math.pi, n, device=device)
+    k = torch.arange(-modes, modes + 1, device=device, dtype=torch.float32)
+    sx, cx = torch.sin(k[:, None] * x[None]), torch.cos(k[:, None] * x[None])          # [2m+1, n]
+    a = coef[:, :, 0].to(device).reshape(B, 2 * modes + 1, 2 * modes + 1)
+    c = coef[:, :, 1].to(device).reshape(B, 2 * modes + 1, 2 * modes + 1)
+    # a*sin(kx+ly) + c*cos(kx+ly) through the angle-sum identities: 4 small contractions
+    f = (torch.einsum("nkl,ki,lj->nij", a, sx, cx) + torch.einsum("nkl,ki,lj->nij", a, cx, sx)
+         + torch.einsum("nkl,ki,lj->nij", c, cx, cx) - torch.einsum("nkl,ki,lj->nij", c, sx, sx))
+    lo = f.amin(dim=(1, 2), keepdim=True)
+    hi = f.amax(dim=(1, 2), keepdim=True)
+    return ((f - lo) / (hi - lo) + 0.1).unsqueeze(1).contiguous()
+
+
+class SnapshotWriter:
+    """Device-staged, side-stream D2H of (u, v) snapshots into one pinned host tensor
+    ``[B, T, 2, H, W]`` -- hides the only D2H of the generator (operators.py:479-482)."""
+
+    def __init__(self, B: int, T: int, H: int, W: int, device):
+        self.host = torch.empty((B, T, 2, H, W), dtype=torch.float32, pin_memory=True)
+        self.stage = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self.done = torch.cuda.Event()
+        self.done.record(self.side)
+        self.count = 0
+
+    def __call__(self, i: int, u: torch.Tensor, v: torch.Tensor) -> None:
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.done)                      # previous D2H has drained the staging buffer
+        self.stage[:, 0].copy_(u.reshape(self.stage[:, 0].shape))
+        self.stage[:, 1].copy_(v.reshape(self.stage[:, 1].shape))
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            self.host[:, self.count].copy_(self.stage, non_blocking=True)
+            self.done.record(self.side)
+        self.count += 1
+
+    def finish(self) -> torch.Tensor:
+        self.side.synchronize()
+        return self.host[:, :self.count]
+
+
+def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.025, mu_hi: float = 0.065,
+             steps: int = 20001, every: int = 200, seed: int = 10, mode: str = "as_written",
+             endpoint: bool = True, dt: float = 1e-4, dx: float = 0.0125, device: Optional[torch.device] = None,
+             rank: Optional[int] = None, world_size: Optional[int] = None, graph: bool = True) -> torch.Tensor:
+    """This rank's shard of the dataset as a pinned host tensor [b, T, 2, mesh, mesh].
+    Defaults are the reference's (5 nu x 20 ICs, 257^2, 20 001 steps, snapshot every 200)."""
+    if rank is None or world_size is None:
+        rank, world_size = D.world()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    P = para * repeat
+    lo, hi = D.shard_bounds(P, rank, world_size)
+    b = hi - lo
+    # mu = linspace(lo, hi, para).repeat(repeat)  (operators.py:411-414): sample p has mu[p % para]
+    mu_all = torch.linspace(mu_lo, mu_hi, para).repeat(repeat)
+    mu = mu_all[lo:hi].to(device)
+    coef = D.fourier_coefficients(seed, lo, hi)                     # [b, 2, 81, 2]
+    u0 = fourier_initial_condition(coef[:, 0], mesh, device)
+    v0 = fourier_initial_condition(coef[:, 1], mesh, device)
+    T = len(range(0, steps, every))
+    writer = SnapshotWriter(b, T, mesh, mesh, device)
+    solver = FineBurgers(dt=dt, dx=dx, dy=dx, mode=mode, endpoint=endpoint)
+    solver.run(u0, v0, mu, steps, every=every, graph=graph, sink=writer)
+    return writer.finish()
+
+
+def main(argv=None) -> None:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--mesh", type=int, default=257)
+    ap.add_argument("--para", type=int, default=5)
+    ap.add_argument("--repeat", type=int, default=20)
+    ap.add_argument("--mu-lo", type=float, default=0.025)
+    ap.add_argument("--mu-hi", type=float, default=0.065)
+    ap.add_argument("--steps", type=int, default=20001)
+    ap.add_argument("--every", type=int, default=200)
+    ap.add_argument("--seed", type=int, default=10)
+    ap.add_argument("--mode", default="as_written", choices=["as_written", "intended"])
+    ap.add_argument("--true-periodic", action="store_true", help="grid without the duplicated endpoint")
+    ap.add_argument("--gather", action="store_true", help="gather all shards into one file on rank 0")
+    a = ap.parse_args(argv)
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, ws = D.world()
+    data = generate(a.mesh, a.para, a.repeat, a.mu_lo, a.mu_hi, a.steps, a.every, a.seed, a.mode,
+                    not a.true_periodic)
+    if a.gather and ws > 1:
+        full = D.gather_shards(data.cuda(), a.para * a.repeat)
+        if rank == 0:
+            torch.save({"u": full.cpu()}, a.out)
+    else:
+        torch.save({"u": data.clone()}, D.shard_file(a.out, rank, ws))
+    if ws > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""Multi-GPU plumbing for the PDE-preserving path: one process per GPU
+(``torchrun``), samples sharded across ranks, NO collective on the data path.
+
+Every sample (trajectory / parameter value / initial condition) is independent
+(SURVEY.md 8(e)), so dataset generation, the ``pde_du`` precompute and rollouts
+shard by sample.  The only exchanges are off the hot path:
+
+* dataset normalisation statistics (train2D.py:115-151 computes per-channel
+  mean / std over the WHOLE dataset): an all-reduce of per-channel count / sum /
+  sum of squares (``channel_stats``);
+* NN gradients in training: ``torch.nn.parallel.DistributedDataParallel`` over NCCL
+  (not here -- the networks stay plain PyTorch).
+
+Works with any backend (``nccl`` on the B200 box, ``gloo`` in the CPU tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the running job; (0, 1) when not distributed."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced shard ``[lo, hi)`` of ``n`` samples for ``rank``: the first
+    ``n % world_size`` ranks own one extra sample, the union over ranks is ``[0, n)``."""
+    if world_size < 1 or not (0 <= rank < world_size) or n < 0:
+        raise ValueError(f"bad shard request n={n} rank={rank} world={world_size}")
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sample_generator(seed: int, global_index: int, device="cpu") -> torch.Generator:
+    """RNG stream of ONE sample, derived from its GLOBAL index, so that the union of
+    the shards is bit-identical to the single-process run whatever the world size."""
+    g = torch.Generator(device=device)
+    g.manual_seed((int(seed) * 1_000_003 + int(global_index)) % (2 ** 63 - 1))
+    return g
+
+
+def fourier_coefficients(seed: int, lo: int, hi: int, modes: int = 4) -> torch.Tensor:
+    """[hi-lo, 2 fields, (2*modes+1)^2, 2] N(0,1) coefficients of the reference's random
+    Fourier initial condition (operators.py:436-441), one RNG stream per global sample."""
+    m = (2 * modes + 1) ** 2
+    out = torch.empty(hi - lo, 2, m, 2)
+    for k, idx in enumerate(range(lo, hi)):
+        out[k] = torch.randn(2, m, 2, generator=sample_generator(seed, idx))
+    return out
+
+
+def channel_stats(x: torch.Tensor, dims: Sequence[int] = (0, 2, 3), group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-channel mean and (unbiased, like ``Tensor.std``) standard deviation of the
+    GLOBAL dataset from local shards ``x`` [b, C, H, W]: one all-reduce of
+    (count, sum, sum of squares) in fp64.  Shapes are ``[1, C, 1, 1]`` like
+    train2D.py:115-116."""
+    xd = x.double()
+    cnt = torch.tensor([float(xd.numel() // xd.shape[1])], dtype=torch.float64, device=x.device)
+    s1 = xd.sum(dim=tuple(dims))
+    s2 = (xd * xd).sum(dim=tuple(dims))
+    buf = torch.cat((cnt, s1, s2))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    c = x.shape[1]
+    n, s1, s2 = buf[0], buf[1:1 + c], buf[1 + c:]
+    mean = s1 / n
+    var = (s2 - n * mean * mean) / (n - 1)
+    shape = [1, c] + [1] * (x.dim() - 2)
+    return mean.float().reshape(shape), var.clamp_min(0).sqrt().float().reshape(shape)
+
+
+def gather_shards(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
+    """Concatenate the per-rank shards (possibly ragged) on rank 0 (None elsewhere)."""
+    rank, ws = world()
+    if ws == 1 or not (dist.is_available() and dist.is_initialized()):
+        return local
+    sizes = [shard_bounds(n_total, r, ws) for r in range(ws)]
+    pieces = [torch.empty((hi - lo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+              for lo, hi in sizes] if rank == 0 else None
+    dist.gather(local.contiguous(), pieces, dst=0, group=group)
+    return torch.cat(pieces, dim=0) if rank == 0 else None
+
+
+def shard_file(path: str, rank: int, world_size: int) -> str:
+    """File name of one rank's shard: ``data.pt`` -> ``data.rank003-of-008.pt``."""
+    if world_size == 1:
+        return path
+    root, ext = os.path.splitext(path)
+    return f"{root}.rank{rank:03d}-of-{world_size:03d}{ext}"
+
+
+def merge_shard_files(path: str, world_size: int, key: str = "u") -> torch.Tensor:
+    """Merge per-rank ``{'u': tensor}`` files (reference wire format, train2D.py:86)."""
+    parts = [torch.load(shard_file(path, r, world_size), map_location="cpu")[key] for r in range(world_size)]
+    return torch.cat(parts, dim=0)

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppnn_b200.so")
+LIB_PATH = os.environ.get("PPNN_B200_LIB") or os.path.join(_HERE, "libppnn_b200.so")
 ABI_VERSION = 1
 
 # enums of include/ppnn_b200.h

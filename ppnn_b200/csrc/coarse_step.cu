@@ -1,21 +1,28 @@
 // Fused coarse-grid PPNN step, forward:  pde_du (src/train2D.py:66-79) and the
 // two kernels of one rollout step around the trainable network
-// (src/train2D.py:230-245).  One CTA owns one sample:
+// (src/train2D.py:230-245).  One CTA (16 warps, 2 resident per SM) owns one sample:
 //
 //   phase 1  bilinear restriction gather of both fields into shared memory
 //            (mesh_convertor.down + [:, :, :-1, :-1])
 //   phase 2  dt * rhs on the periodic N x N coarse grid, still in shared memory
 //            (padbcx/padbcy wrap, Upwind1 / Central2 stencils, rhs.py algebra)
-//   phase 3  stream the fine grid once: every warp takes (field, 32-column
-//            chunk, row band) strips, keeps a 4-row window of y-interpolated
-//            coarse values in registers (padBC_rd + bicubic, W pass then H pass
-//            like torch) and fuses the epilogue (pdeu | normalised net inputs |
-//            explicit update with the network output) into the store.
+//   phase 3  stream the fine grid once.  The duplicated-endpoint column (one
+//            element per row) is evaluated directly, one point per thread; the
+//            other FW-1 columns are whole warps wide: every warp takes (field,
+//            32-column chunk, row band) strips, lane = column, and walks down the
+//            rows with a 4-row register window of W-interpolated coarse values
+//            (padBC_rd + bicubic, W pass then H pass like torch), a rolling
+//            kDepth-row register prefetch of the streamed operands and the
+//            epilogue (pdeu | normalised net inputs | explicit update with the
+//            network output) fused into the store.  The fine width is a template
+//            parameter for the reference mesh (257) so that every streamed access
+//            is base + immediate.
 //
-// HBM-bound by construction: per fine point the update kernel reads u and
-// nn_out once and writes u_next once (12 B); the restriction gather re-reads
-// (F-1)/(C-1)-strided rows only.  No tensor cores: 1-channel 3..9-tap stencils
-// and a 4x4 separable interpolation have no dense contraction to feed them.
+// HBM-bound by construction: per fine point the update kernel reads u and nn_out
+// once and writes u_next once (12 B); the restriction gather re-reads
+// (F-1)/(C-1)-strided rows only (L2 hits).  No tensor cores: 1-channel 3..9-tap
+// stencils and a separable 4x4 interpolation have no dense contraction.
+#include <cstdlib>
 #include "coarse_common.cuh"
 
 namespace ppnn {
@@ -33,34 +40,58 @@ struct StepIO {
     float m1[2], s1[2];    // pdemean/pdestd (INPUTS)
 };
 
-constexpr int kRowUnroll = 8;
+struct StepPlan {
+    int wmain;             // columns handled by strips (FW-1 when that is a multiple of 32, else FW)
+    int nchunk, nband, band_rows;
+};
 
-template <int MODE>
-__global__ void __launch_bounds__(512, 2)
-coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
-    extern __shared__ float smem[];
+#ifndef PPNN_STEP_WARPS
+#define PPNN_STEP_WARPS 16
+#endif
+#ifndef PPNN_MINCTA
+#define PPNN_MINCTA 2
+#endif
+#ifndef PPNN_DEPTH
+#define PPNN_DEPTH 4
+#endif
+constexpr int kStepThreads = PPNN_STEP_WARPS * 32;
+constexpr int kDepth = PPNN_DEPTH;   // rows of streamed operands in flight per lane (register path)
+
+}  // namespace ppnn
+#include "coarse_step_staged.cuh"
+namespace ppnn {
+
+template <int MODE, int FWC>
+__global__ void __launch_bounds__(kStepThreads, PPNN_MINCTA)
+coarse_step_kernel(const CoarseParams p, const StepIO io, const StepPlan pl) {
+    extern __shared__ float4 smem4[];
+    float4* roww = smem4;                                       // [FH] H-pass weights
+    int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
     const int nn2 = p.NH * p.NW;
-    float* cu = smem;
+    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 3) & ~3));
     float* cv = cu + nn2;
     float* ru = cv + nn2;
     float* rv = ru + nn2;
-    float4* roww = reinterpret_cast<float4*>(rv + nn2);     // [FH] x-weights (16 B aligned: 4*nn2 floats)
-    int* rowi = reinterpret_cast<int*>(roww + p.FH);        // [FH] floor(i * suh)
 
+    const int FW = FWC ? FWC : p.FW;                            // compile-time pitch when specialised
+    const int PW = FW - 1, PH = p.FH - 1;                       // network grid (no endpoint)
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const size_t plane = (size_t)p.FH * p.FW;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const size_t plane = (size_t)p.FH * FW;
+    const size_t nplane = (size_t)PH * PW;
     const float* ub = io.u + (size_t)b * 2 * plane;
     const float mu = __ldg(io.mu + b);
 
-    // ---- phase 1: restriction gather ------------------------------------
-    for (int idx = tid; idx < 2 * nn2; idx += nthr) {
+    // ---- phase 1: restriction gather + row tables --------------------------
+#pragma unroll 4
+    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
         int f = idx >= nn2;
         int r = idx - f * nn2;
         int I = r / p.NW, J = r - I * p.NW;
-        cu[idx] = restrict_point(p, ub + f * plane, I, J);     // cv follows cu contiguously
+        cu[idx] = restrict_point(p, ub + f * plane, I, J);       // cv follows cu contiguously
     }
-    for (int i = tid; i < p.FH; i += nthr) {
+    for (int i = tid; i < p.FH; i += kStepThreads) {
         float w[4]; int i0;
         cubic_entry(p.suh, i, &i0, w);
         rowi[i] = i0;
@@ -68,31 +99,62 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
     }
     __syncthreads();
 
-    // ---- phase 2: dt * rhs on the periodic coarse grid --------------------
-    for (int idx = tid; idx < nn2; idx += nthr) {
-        int I = idx / p.NW, J = idx - I * p.NW;
-        ru[idx] = p.dt * eval_rhs(p, p.rhs_u, cu, cu, cv, I, J, mu);
-        rv[idx] = p.dt * eval_rhs(p, p.rhs_v, cv, cu, cv, I, J, mu);
+    // ---- phase 2: dt * rhs on the periodic coarse grid ----------------------
+    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
+        int f = idx >= nn2;
+        int r = idx - f * nn2;
+        int I = r / p.NW, J = r - I * p.NW;
+        ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);
     }
     __syncthreads();
 
-    // ---- phase 3: prolongation + fused epilogue, one strip per warp -------
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int nchunk = (p.FW + 31) >> 5;
-    const int nband = (p.FH + band_rows - 1) / band_rows;
-    const int nstrip = 2 * nband * nchunk;
-    const int PH = p.FH - 1, PW = p.FW - 1;                    // network grid (no endpoint)
-    const size_t nplane = (size_t)PH * PW;
+    // ---- phase 3a: the duplicated-endpoint column, one point per thread -----
+    const bool want_out = MODE == MODE_INPUTS ? io.out != nullptr : true;
+    if (pl.wmain < FW && want_out) {
+        const int jc = FW - 1;
+        float wy[4]; int j0;
+        cubic_entry(p.suw, jc, &j0, wy);
+        const int c0 = ext_index(j0 - 1, p.CW), c1 = ext_index(j0, p.CW),
+                  c2 = ext_index(j0 + 1, p.CW), c3 = ext_index(j0 + 2, p.CW);
+        for (int idx = tid; idx < 2 * p.FH; idx += kStepThreads) {
+            const int f = idx >= p.FH;
+            const int i = idx - f * p.FH;
+            const float* rf = f ? rv : ru;
+            const int i0 = rowi[i];
+            const float4 wx = roww[i];
+            float h[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float* r = rf + ext_index(i0 - 1 + a, p.CH) * p.NW;
+                h[a] = r[c0] * wy[0] + r[c1] * wy[1] + r[c2] * wy[2] + r[c3] * wy[3];
+            }
+            const float pde = h[0] * wx.x + h[1] * wx.y + h[2] * wx.z + h[3] * wx.w;
+            const size_t o = ((size_t)b * 2 + f) * plane + (size_t)i * FW + jc;
+            if (MODE == MODE_UPDATE) {
+                const float uu = ld_stream(io.u + o);
+                float v = uu + pde;
+                if (io.nn) {
+                    const float n = ld_stream(io.nn + ((size_t)b * 2 + f) * nplane + (size_t)(i == PH ? 0 : i) * PW);
+                    v = (n * (f ? io.s0[1] : io.s0[0]) + (f ? io.m0[1] : io.m0[0])) + uu + pde;
+                }
+                st_stream(io.out + o, v);
+            } else {
+                st_stream(io.out + o, pde);
+            }
+        }
+    }
 
-    for (int s = warp; s < nstrip; s += nwarp) {
+    // ---- phase 3b: (field, chunk, band) strips, one per warp at a time ------
+    const int nstrip = 2 * pl.nchunk * pl.nband;
+    for (int s = warp; s < nstrip; s += PPNN_STEP_WARPS) {
         // consecutive warps take consecutive column chunks of the same band
-        const int chunk = s % nchunk;
-        const int t2 = s / nchunk;
+        const int chunk = s % pl.nchunk;
+        const int t2 = s / pl.nchunk;
         const int f = t2 & 1;
         const int band = t2 >> 1;
         const int j = chunk * 32 + lane;
-        const bool active = j < p.FW;
-        const int jc = active ? j : p.FW - 1;
+        const bool active = j < pl.wmain;
+        const int jc = active ? j : pl.wmain - 1;
         const float* rf = f ? rv : ru;
 
         float wy[4]; int j0;
@@ -101,16 +163,15 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
         const float* rc1 = rf + ext_index(j0, p.CW);
         const float* rc2 = rf + ext_index(j0 + 1, p.CW);
         const float* rc3 = rf + ext_index(j0 + 2, p.CW);
-        auto yrow = [&](int I) -> float {     // W-pass of row I of the extended coarse increment
+        auto yrow = [&](int I) -> float {     // W pass of row I of the extended coarse increment
             const int o = ext_index(I, p.CH) * p.NW;
             return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
         };
-
-        const int r0 = band * band_rows;
-        const int r1 = min(r0 + band_rows, p.FH);
+        const int r0 = band * pl.band_rows;
+        const int r1 = band == pl.nband - 1 ? p.FH : r0 + pl.band_rows;
         int base = rowi[r0];
         float h0 = yrow(base - 1), h1 = yrow(base), h2 = yrow(base + 1), h3 = yrow(base + 2);
-        // H-pass of fine row ii (advances the window when floor(ii*suh) moves on; warp-uniform)
+        // H pass of fine row ii; the window advances when floor(ii*suh) moves on (warp-uniform)
         auto prolong = [&](int ii) -> float {
             const int i0 = rowi[ii];
             const float4 wx = roww[ii];
@@ -124,88 +185,98 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, int band_rows) {
 
         const float m0 = f ? io.m0[1] : io.m0[0], s0 = f ? io.s0[1] : io.s0[0];
         const float m1 = f ? io.m1[1] : io.m1[0], s1 = f ? io.s1[1] : io.s1[0];
-        const size_t off = ((size_t)b * 2 + f) * plane + (size_t)r0 * p.FW + jc;
-        const float* up = io.u + off;                          // row pointers, bumped by one pitch per row
-        float* op = io.out ? io.out + off : nullptr;
+        const size_t foff = ((size_t)b * 2 + f) * plane + (size_t)r0 * FW + jc;
+        const size_t noff = ((size_t)b * 2 + f) * nplane + (size_t)r0 * PW;
+        const float* up = io.u + foff;                         // row-r0 pointers, bumped kDepth rows at a time
+        float* op = io.out ? io.out + foff : nullptr;
 
         if (MODE == MODE_PDEU) {
-            for (int ii = r0; ii < r1; ++ii, op += p.FW) {
-                float pde = prolong(ii);
+            for (int ii = r0; ii < r1; ++ii, op += FW) {
+                const float pde = prolong(ii);
                 if (active) st_stream(op, pde);
             }
         } else if (MODE == MODE_UPDATE) {
             const bool has_nn = io.nn != nullptr;
             const int jn = jc == PW ? 0 : jc;                  // padBC_rd column fold
-            const float* nbase = has_nn ? io.nn + ((size_t)b * 2 + f) * nplane + jn : nullptr;
-            const float* np = has_nn ? nbase + (size_t)r0 * PW : nullptr;
-            const int rmain = min(r1, PH);                     // rows whose network row is the row itself
-            int ii = r0;
-            for (; ii + kRowUnroll <= rmain; ii += kRowUnroll) {
-                float uu[kRowUnroll], nv[kRowUnroll];
-                if (active) {
+            const float* np = has_nn ? io.nn + noff + jn : nullptr;
+            const int rn = min(r1, PH);                        // rows whose network row is the row itself
+            // double-buffered batches of kDepth rows: batch B is in flight while batch A is consumed
+            float ua[kDepth], na[kDepth], ub2[kDepth], nb[kDepth];
+            auto load = [&](float (&uu)[kDepth], float (&nv)[kDepth], int first, int rowoff) {
 #pragma unroll
-                    for (int q = 0; q < kRowUnroll; ++q) uu[q] = ld_stream(up + (size_t)q * p.FW);
-                    if (has_nn) {
+                for (int q = 0; q < kDepth; ++q) {
+                    const bool ok = active && first + q < rn;
+                    uu[q] = ok ? ld_stream(up + (size_t)(rowoff + q) * FW) : 0.f;
+                    nv[q] = (ok && has_nn) ? ld_stream(np + (size_t)(rowoff + q) * PW) : 0.f;
+                }
+            };
+            auto consume = [&](const float (&uu)[kDepth], const float (&nv)[kDepth], int first, int rowoff) {
 #pragma unroll
-                        for (int q = 0; q < kRowUnroll; ++q) nv[q] = ld_stream(np + (size_t)q * PW);
+                for (int q = 0; q < kDepth; ++q) {
+                    if (first + q < rn) {                       // warp-uniform
+                        const float pde = prolong(first + q);
+                        const float v = has_nn ? (nv[q] * s0 + m0) + uu[q] + pde : uu[q] + pde;
+                        if (active) st_stream(op + (size_t)(rowoff + q) * FW, v);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < kRowUnroll; ++q) {
-                    float pde = prolong(ii + q);
-                    if (active) {
-                        float v = has_nn ? (nv[q] * s0 + m0) + uu[q] + pde : uu[q] + pde;
-                        st_stream(op + (size_t)q * p.FW, v);
-                    }
-                }
-                up += (size_t)kRowUnroll * p.FW; op += (size_t)kRowUnroll * p.FW;
-                if (has_nn) np += (size_t)kRowUnroll * PW;
+            };
+            load(ua, na, r0, 0);
+            for (int ii = r0; ii < rn; ii += 2 * kDepth) {
+                load(ub2, nb, ii + kDepth, kDepth);
+                consume(ua, na, ii, 0);
+                load(ua, na, ii + 2 * kDepth, 2 * kDepth);
+                consume(ub2, nb, ii + kDepth, kDepth);
+                up += (size_t)2 * kDepth * FW; op += (size_t)2 * kDepth * FW;
+                if (has_nn) np += (size_t)2 * kDepth * PW;
             }
-            for (; ii < r1; ++ii, up += p.FW, op += p.FW) {    // ragged tail and the endpoint row
-                float pde = prolong(ii);
+            if (r1 > rn) {                                      // the endpoint row: network row 0 (padBC_rd)
+                const float pde = prolong(PH);
                 if (active) {
-                    float uu = ld_stream(up);
-                    float v = uu + pde;
-                    if (has_nn) v = (ld_stream(nbase + (size_t)(ii == PH ? 0 : ii) * PW) * s0 + m0) + uu + pde;
-                    st_stream(op, v);
+                    const size_t o = ((size_t)b * 2 + f) * plane + (size_t)PH * FW + jc;
+                    const float u0 = ld_stream(io.u + o);
+                    float v = u0 + pde;
+                    if (has_nn) v = (ld_stream(io.nn + ((size_t)b * 2 + f) * nplane + jn) * s0 + m0) + u0 + pde;
+                    st_stream(io.out + o, v);
                 }
             }
         } else {   // MODE_INPUTS
             const float rs0 = 1.f / s0, rs1 = 1.f / s1;
             const bool colok = active && jc < PW;
-            float* unp = io.u_norm + ((size_t)b * 2 + f) * nplane + (size_t)r0 * PW + jc;
-            float* pnp = io.p_norm ? io.p_norm + ((size_t)b * 2 + f) * nplane + (size_t)r0 * PW + jc : nullptr;
-            const int rmain = min(r1, PH);
-            int ii = r0;
-            for (; ii + kRowUnroll <= rmain; ii += kRowUnroll) {
-                float uu[kRowUnroll];
-                if (colok) {
+            float* unp = io.u_norm + noff + jc;
+            float* pnp = io.p_norm ? io.p_norm + noff + jc : nullptr;
+            const int rn = min(r1, PH);                        // rows of the network grid in this band
+            float ua[kDepth], ub2[kDepth];
+            auto load = [&](float (&uu)[kDepth], int first, int rowoff) {
 #pragma unroll
-                    for (int q = 0; q < kRowUnroll; ++q) uu[q] = ld_stream(up + (size_t)q * p.FW);
-                }
+                for (int q = 0; q < kDepth; ++q)
+                    uu[q] = (colok && first + q < rn) ? ld_stream(up + (size_t)(rowoff + q) * FW) : 0.f;
+            };
+            auto consume = [&](const float (&uu)[kDepth], int first, int rowoff) {
 #pragma unroll
-                for (int q = 0; q < kRowUnroll; ++q) {
-                    float pde = prolong(ii + q);
-                    if (op && active) st_stream(op + (size_t)q * p.FW, pde);
-                    if (colok) {
-                        st_stream(unp + (size_t)q * PW, div_by(uu[q] - m0, s0, rs0));
-                        if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
+                for (int q = 0; q < kDepth; ++q) {
+                    if (first + q < rn) {
+                        const float pde = prolong(first + q);
+                        if (op && active) st_stream(op + (size_t)(rowoff + q) * FW, pde);
+                        if (colok) {
+                            st_stream(unp + (size_t)(rowoff + q) * PW, div_by(uu[q] - m0, s0, rs0));
+                            if (pnp) st_stream(pnp + (size_t)(rowoff + q) * PW, div_by(pde - m1, s1, rs1));
+                        }
                     }
                 }
-                up += (size_t)kRowUnroll * p.FW; unp += (size_t)kRowUnroll * PW;
-                if (op) op += (size_t)kRowUnroll * p.FW;
-                if (pnp) pnp += (size_t)kRowUnroll * PW;
+            };
+            load(ua, r0, 0);
+            for (int ii = r0; ii < rn; ii += 2 * kDepth) {
+                load(ub2, ii + kDepth, kDepth);
+                consume(ua, ii, 0);
+                load(ua, ii + 2 * kDepth, 2 * kDepth);
+                consume(ub2, ii + kDepth, kDepth);
+                up += (size_t)2 * kDepth * FW; unp += (size_t)2 * kDepth * PW;
+                if (op) op += (size_t)2 * kDepth * FW;
+                if (pnp) pnp += (size_t)2 * kDepth * PW;
             }
-            for (; ii < r1; ++ii) {
-                float pde = prolong(ii);
-                if (op && active) st_stream(op, pde);
-                if (colok && ii < PH) {
-                    st_stream(unp, div_by(ld_stream(up) - m0, s0, rs0));
-                    if (pnp) st_stream(pnp, div_by(pde - m1, s1, rs1));
-                }
-                up += p.FW; unp += PW;
-                if (op) op += p.FW;
-                if (pnp) pnp += PW;
+            if (r1 > rn && op) {                                // endpoint row exists only in pdeu
+                const float pde = prolong(PH);
+                if (active) st_stream(io.out + ((size_t)b * 2 + f) * plane + (size_t)PH * FW + jc, pde);
             }
         }
     }
@@ -243,7 +314,17 @@ coarse_increment_kernel(const CoarseParams p, const float* __restrict__ uc, cons
 }
 
 static size_t step_smem_bytes(const CoarseParams& p) {
-    return (size_t)4 * p.NH * p.NW * sizeof(float) + (size_t)p.FH * (sizeof(float4) + sizeof(int));
+    return (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 3) & ~3) * sizeof(int) +
+           (size_t)4 * p.NH * p.NW * sizeof(float);
+}
+
+template <int MODE, int FWC>
+static int launch_step_fw(const CoarseParams& p, const StepIO& io, const StepPlan& pl, int B, size_t smem, void* stream) {
+    auto kern = coarse_step_kernel<MODE, FWC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<B, kStepThreads, smem, (cudaStream_t)stream>>>(p, io, pl);
+    return launch_status();
 }
 
 template <int MODE>
@@ -255,19 +336,44 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     if (B == 0) return PPNN_OK;
     size_t smem = step_smem_bytes(p);
     if (smem > 200 * 1024) return PPNN_E_TOOBIG;
-    auto kern = coarse_step_kernel<MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    // strips: 2 fields x ceil(FW/32) chunks x bands; aim at >= 2 strips per warp
-    int nchunk = (p.FW + 31) / 32;
-    int nband = (p.FH + 63) / 64;
-    int band_rows = (p.FH + nband - 1) / nband;
-    band_rows = (band_rows + kRowUnroll - 1) / kRowUnroll * kRowUnroll;
-    int nstrip = 2 * nchunk * ((p.FH + band_rows - 1) / band_rows);
-    int warps = nstrip < 16 ? nstrip : 16;
-    if (warps < 4) warps = 4;
-    kern<<<B, warps * 32, smem, (cudaStream_t)stream>>>(p, io, band_rows);
-    return launch_status();
+    StepPlan pl;
+    // the duplicated-endpoint column is evaluated point-wise when the rest is whole warps wide
+    pl.wmain = ((p.FW - 1) % 32 == 0) ? p.FW - 1 : p.FW;
+    pl.nchunk = (pl.wmain + 31) / 32;
+    // bands so that 2 * nchunk * nband strips fill the warps evenly (2 strips per warp)
+    pl.nband = (2 * PPNN_STEP_WARPS + 2 * pl.nchunk - 1) / (2 * pl.nchunk);
+    int max_band = (p.FH + 4 * kDepth - 1) / (4 * kDepth);
+    if (pl.nband > max_band) pl.nband = max_band;
+    if (pl.nband < 1) pl.nband = 1;
+    pl.band_rows = (p.FH - 1) / pl.nband;                      // the last band takes the remainder
+    if (pl.band_rows < 1) { pl.band_rows = p.FH; pl.nband = 1; }
+    // TMA-staged path: operands through a shared-memory ring (see coarse_step_staged.cuh)
+    const bool nn_ok = !io.nn || (reinterpret_cast<uintptr_t>(io.nn) & 15) == 0;
+    if (MODE != MODE_PDEU && 2 * pl.nchunk <= PPNN_STEP_WARPS && (p.FW - 1) % 4 == 0 && nn_ok && !getenv("PPNN_NO_TMA")) {
+        StagedLayout lay;
+        lay.ustage = (kStageRows * p.FW + 8 + 3) & ~3;
+        lay.nstage = (MODE == MODE_UPDATE && io.nn) ? kStageRows * (p.FW - 1) : 0;
+        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 3) & ~3) * sizeof(int) +
+                       (size_t)((4 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
+                       (size_t)kStages * 2 * (lay.ustage + lay.nstage) * sizeof(float);
+        if (smem2 <= 200 * 1024) {
+            const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
+            if (p.FW == 257) {
+                auto kern = coarse_step_staged_kernel<MODE, 257>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                if (e != cudaSuccess) return (int)e;
+                kern<<<B, kStepThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
+            } else {
+                auto kern = coarse_step_staged_kernel<MODE, 0>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                if (e != cudaSuccess) return (int)e;
+                kern<<<B, kStepThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
+            }
+            return launch_status();
+        }
+    }
+    if (p.FW == 257) return launch_step_fw<MODE, 257>(p, io, pl, B, smem, stream);
+    return launch_step_fw<MODE, 0>(p, io, pl, B, smem, stream);
 }
 
 }  // namespace ppnn

@@ -1,0 +1,270 @@
+// TMA-staged variant of the fused coarse step (MODE_UPDATE / MODE_INPUTS) for
+// meshes of at most 256 + 1 columns -- the reference mesh, 257.
+//
+// Same phases as coarse_step_kernel, but the streamed operands (u and nn_out) do
+// not go through registers: one elected thread feeds a 2-stage shared-memory
+// ring with `cp.async.bulk` (TMA, 1-D) copies of kStageRows-row bands of both
+// field planes, completion is signalled on an mbarrier, and the 16 warps (field,
+// 32-column chunk) read their operands with LDS.  The first two stages are
+// issued at kernel entry, so they are in flight while the latency-bound
+// restriction gather and the coarse RHS run.  Long-scoreboard (global-load)
+// stalls in the hot loop become short shared-memory ones, and the prefetch
+// depth is no longer bounded by registers or by the six scoreboard slots.
+//
+// Alignment: a band of rows of a [.., 257, 257] plane starts at a 4-byte, not a
+// 16-byte, boundary.  Each copy therefore starts at the enclosing 16-byte
+// boundary and the consumer skips `lead` = 0..3 floats; the last copy of the
+// tensor is clamped to its 16-byte-aligned end and the few trailing floats are
+// fetched with ordinary loads, so nothing outside the tensor is ever read.
+#pragma once
+#include "coarse_common.cuh"
+
+namespace ppnn {
+
+constexpr int kStageRows = 8;
+constexpr int kStages = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct StagedLayout {
+    int ustage;      // floats per (stage, field) u buffer: kStageRows*FW + 8 (lead / tail slack), 16 B multiple
+    int nstage;      // floats per (stage, field) nn buffer: kStageRows*PW
+};
+
+template <int MODE, int FWC>
+__global__ void __launch_bounds__(kStepThreads, PPNN_MINCTA)
+coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
+                          const float* u_end) {
+    extern __shared__ float4 smem4[];
+    float4* roww = smem4;                                       // [FH] H-pass weights
+    int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
+    const int nn2 = p.NH * p.NW;
+    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 3) & ~3));
+    float* cv = cu + nn2;
+    float* ru = cv + nn2;
+    float* rv = ru + nn2;
+    float* sU = cu + ((4 * nn2 + 3) & ~3);                      // [kStages][2][ustage], 16-byte aligned
+    float* sN = sU + (size_t)kStages * 2 * lay.ustage;          // [kStages][2][nstage]
+    __shared__ __align__(8) uint64_t full[kStages];
+
+    const int FW = FWC ? FWC : p.FW;
+    const int PW = FW - 1, PH = p.FH - 1;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const size_t plane = (size_t)p.FH * FW;
+    const size_t nplane = (size_t)PH * PW;
+    const float* ub = io.u + (size_t)b * 2 * plane;
+    const float mu = __ldg(io.mu + b);
+    const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
+    const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
+
+    // producer (thread 0): bulk copies of step t into ring slot t % kStages
+    auto issue = [&](int t) {
+        const int s = t % kStages;
+        const int r0 = t * kStageRows;
+        const int nrows = min(kStageRows, p.FH - r0);
+        uintptr_t a0[2]; uint32_t nb[2]; uint32_t total = 0;
+        const uintptr_t end_al = reinterpret_cast<uintptr_t>(u_end) & ~(uintptr_t)15;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(ub + f * plane + (size_t)r0 * FW);
+            a0[f] = a & ~(uintptr_t)15;
+            nb[f] = (uint32_t)((a - a0[f]) + (size_t)nrows * FW * 4 + 15) & ~15u;
+            if (a0[f] + nb[f] > end_al) {                       // last copy of the tensor: stay inside it
+                const uint32_t inside = (uint32_t)(end_al - a0[f]);
+                float* dst = sU + ((size_t)s * 2 + f) * lay.ustage;
+                for (const float* q = reinterpret_cast<const float*>(end_al); q < u_end; ++q)
+                    dst[(reinterpret_cast<uintptr_t>(q) - a0[f]) >> 2] = *q;
+                nb[f] = inside;
+            }
+            total += nb[f];
+        }
+        const int nr0 = r0 < PH ? r0 : 0;                       // the endpoint row uses network row 0 (padBC_rd)
+        const int nnrows = r0 < PH ? min(kStageRows, PH - r0) : 1;
+        const uint32_t nnb = (uint32_t)nnrows * PW * 4;
+        if (has_nn) total += 2 * nnb;
+        mbar_expect_tx(&full[s], total);
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            if (nb[f]) bulk_g2s(sU + ((size_t)s * 2 + f) * lay.ustage, reinterpret_cast<const void*>(a0[f]), nb[f], &full[s]);
+            if (has_nn)
+                bulk_g2s(sN + ((size_t)s * 2 + f) * lay.nstage,
+                         io.nn + ((size_t)b * 2 + f) * nplane + (size_t)nr0 * PW, nnb, &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+        for (int t = 0; t < kStages && t < nsteps; ++t) issue(t);   // in flight during phases 1 and 2
+    }
+
+    // ---- phase 1: restriction gather + row tables --------------------------
+#pragma unroll 4
+    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
+        int f = idx >= nn2;
+        int r = idx - f * nn2;
+        int I = r / p.NW, J = r - I * p.NW;
+        cu[idx] = restrict_point(p, ub + f * plane, I, J);
+    }
+    for (int i = tid; i < p.FH; i += kStepThreads) {
+        float w[4]; int i0;
+        cubic_entry(p.suh, i, &i0, w);
+        rowi[i] = i0;
+        roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+
+    // ---- phase 2: dt * rhs on the periodic coarse grid ----------------------
+    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
+        int f = idx >= nn2;
+        int r = idx - f * nn2;
+        int I = r / p.NW, J = r - I * p.NW;
+        ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);
+    }
+    __syncthreads();
+
+    // ---- phase 3a: the duplicated-endpoint column, one point per thread -----
+    const bool want_out = MODE == MODE_INPUTS ? io.out != nullptr : true;
+    if (pl.wmain < FW && want_out) {
+        const int jc = FW - 1;
+        float wy[4]; int j0;
+        cubic_entry(p.suw, jc, &j0, wy);
+        const int c0 = ext_index(j0 - 1, p.CW), c1 = ext_index(j0, p.CW),
+                  c2 = ext_index(j0 + 1, p.CW), c3 = ext_index(j0 + 2, p.CW);
+        for (int idx = tid; idx < 2 * p.FH; idx += kStepThreads) {
+            const int f = idx >= p.FH;
+            const int i = idx - f * p.FH;
+            const float* rf = f ? rv : ru;
+            const int i0 = rowi[i];
+            const float4 wx = roww[i];
+            float h[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float* r = rf + ext_index(i0 - 1 + a, p.CH) * p.NW;
+                h[a] = r[c0] * wy[0] + r[c1] * wy[1] + r[c2] * wy[2] + r[c3] * wy[3];
+            }
+            const float pde = h[0] * wx.x + h[1] * wx.y + h[2] * wx.z + h[3] * wx.w;
+            const size_t o = ((size_t)b * 2 + f) * plane + (size_t)i * FW + jc;
+            if (MODE == MODE_UPDATE) {
+                const float uu = ld_stream(io.u + o);
+                float v = uu + pde;
+                if (has_nn) {
+                    const float n = ld_stream(io.nn + ((size_t)b * 2 + f) * nplane + (size_t)(i == PH ? 0 : i) * PW);
+                    v = (n * (f ? io.s0[1] : io.s0[0]) + (f ? io.m0[1] : io.m0[0])) + uu + pde;
+                }
+                st_stream(io.out + o, v);
+            } else {
+                st_stream(io.out + o, pde);
+            }
+        }
+    }
+
+    // ---- phase 3b: warp = (field, 32-column chunk), all rows, operands from the ring --
+    const int f = warp / pl.nchunk;
+    const int chunk = warp - f * pl.nchunk;
+    const bool mine = f < 2;                                    // spare warps only keep the barriers company
+    const int j = chunk * 32 + lane;
+    const bool active = mine && j < pl.wmain;
+    const int jc = j < pl.wmain ? j : pl.wmain - 1;
+    const int jn = jc == PW ? 0 : jc;                           // padBC_rd column fold
+    const float* rf = (f & 1) ? rv : ru;
+
+    float wy[4]; int j0;
+    cubic_entry(p.suw, jc, &j0, wy);
+    const float* rc0 = rf + ext_index(j0 - 1, p.CW);
+    const float* rc1 = rf + ext_index(j0, p.CW);
+    const float* rc2 = rf + ext_index(j0 + 1, p.CW);
+    const float* rc3 = rf + ext_index(j0 + 2, p.CW);
+    auto yrow = [&](int I) -> float {
+        const int o = ext_index(I, p.CH) * p.NW;
+        return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
+    };
+    int base = rowi[0];
+    float h0 = yrow(base - 1), h1 = yrow(base), h2 = yrow(base + 1), h3 = yrow(base + 2);
+    auto prolong = [&](int ii) -> float {
+        const int i0 = rowi[ii];
+        const float4 wx = roww[ii];
+        if (i0 != base) {
+            if (i0 == base + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = yrow(i0 + 2); }
+            else { h0 = yrow(i0 - 1); h1 = yrow(i0); h2 = yrow(i0 + 1); h3 = yrow(i0 + 2); }
+            base = i0;
+        }
+        return h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w;
+    };
+
+    const int fc = mine ? f : 0;
+    const float m0 = fc ? io.m0[1] : io.m0[0], s0 = fc ? io.s0[1] : io.s0[0];
+    const float m1 = fc ? io.m1[1] : io.m1[0], s1 = fc ? io.s1[1] : io.s1[0];
+    const float rs0 = 1.f / s0, rs1 = 1.f / s1;
+    const size_t foff = ((size_t)b * 2 + fc) * plane + jc;
+    const size_t noff = ((size_t)b * 2 + fc) * nplane + jc;
+    float* op = io.out ? io.out + foff : nullptr;
+    float* unp = MODE == MODE_INPUTS ? io.u_norm + noff : nullptr;
+    float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + noff : nullptr;
+    const bool colok = active && jc < PW;
+
+    for (int t = 0; t < nsteps; ++t) {
+        const int s = t % kStages;
+        const int r0 = t * kStageRows;
+        mbar_wait(&full[s], (t / kStages) & 1);
+        if (mine) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(ub + fc * plane + (size_t)r0 * FW);
+            const int lead = (int)(a & 15) >> 2;
+            const float* su = sU + ((size_t)s * 2 + fc) * lay.ustage + lead + jc;
+            const float* sn = sN + ((size_t)s * 2 + fc) * lay.nstage + jn;
+#pragma unroll
+            for (int q = 0; q < kStageRows; ++q) {
+                const int row = r0 + q;
+                if (row < p.FH) {                               // warp-uniform
+                    const float pde = prolong(row);
+                    const float uu = su[q * FW];
+                    if (MODE == MODE_UPDATE) {
+                        const float v = has_nn ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
+                        if (active) st_stream(op + (size_t)row * FW, v);
+                    } else {
+                        if (op && active) st_stream(op + (size_t)row * FW, pde);
+                        if (colok && row < PH) {
+                            st_stream(unp + (size_t)row * PW, div_by(uu - m0, s0, rs0));
+                            if (pnp) st_stream(pnp + (size_t)row * PW, div_by(pde - m1, s1, rs1));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                        // slot s is free again
+        if (tid == 0 && t + kStages < nsteps) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + kStages);
+        }
+    }
+}
+
+}  // namespace ppnn

@@ -21,6 +21,7 @@ struct CoarseParams {
     float adv_b[4];      // Backward1[acc] at offsets -acc..0
     float diff[kMaxTaps];
     float dt, dx, dy, dx2, dy2;
+    float rdx, rdy, rdx2, rdy2;   // fp32 reciprocals (for the correctly rounded fast division)
     float sdh, sdw;      // restriction scales (F-1)/(C-1)
     float suh, suw;      // prolongation scales (C-1)/(F-1)
 };
@@ -44,6 +45,7 @@ inline int fill_coarse_params(const ppnn_coarse_cfg* cfg, CoarseParams* p) {
     p->diff_n = d.n; p->diff_off = d.off;
     for (int k = 0; k < kMaxTaps; ++k) p->diff[k] = d.c[k];
     p->dt = cfg->dt; p->dx = cfg->dx; p->dy = cfg->dy; p->dx2 = cfg->dx2; p->dy2 = cfg->dy2;
+    p->rdx = 1.f / cfg->dx; p->rdy = 1.f / cfg->dy; p->rdx2 = 1.f / cfg->dx2; p->rdy2 = 1.f / cfg->dy2;
     p->sdh = resample_scale(cfg->FH, cfg->CH, true);
     p->sdw = resample_scale(cfg->FW, cfg->CW, true);
     p->suh = resample_scale(cfg->CH, cfg->FH, true);
@@ -137,12 +139,65 @@ __device__ __forceinline__ float eval_rhs(const CoarseParams& p, int id, const f
     float u1 = cu[I * p.NW + J], v1 = cv[I * p.NW + J];
     float acc = 0.f;
     if (id & PPNN_RHS_ADV)
-        acc = (-u1 * upwind_x(p, f, I, J)) / p.dx - (v1 * upwind_y(p, f, I, J)) / p.dy;
+        acc = div_by(-u1 * upwind_x(p, f, I, J), p.dx, p.rdx) - div_by(v1 * upwind_y(p, f, I, J), p.dy, p.rdy);
     if (id & PPNN_RHS_DIFF) {
-        float lap = mu * (central_x(p, f, I, J) / p.dx2 + central_y(p, f, I, J) / p.dy2);
+        float lap = mu * (div_by(central_x(p, f, I, J), p.dx2, p.rdx2) + div_by(central_y(p, f, I, J), p.dy2, p.rdy2));
         acc = (id & PPNN_RHS_ADV) ? acc + lap : lap;
     }
     return add_reaction(acc, id & ~3, u1, v1);
+}
+
+// Both right-hand sides of one coarse point for the stencils every train2D.py case
+// uses (Upwind1 accuracy 1, Central2 accuracy 2; train2D.py:53-56): the four
+// neighbours are fetched once per field and the tap loops disappear.  Same
+// arithmetic as eval_rhs (taps +-1, -2 are exact; sums in tap order).
+__device__ __forceinline__ void eval_rhs_pair_3pt(const CoarseParams& p, const float* cu, const float* cv,
+                                                  int I, int J, float mu, float* out_u, float* out_v) {
+    const int Im = (I == 0 ? p.NH : I) - 1, Ip = I + 1 == p.NH ? 0 : I + 1;
+    const int Jm = (J == 0 ? p.NW : J) - 1, Jp = J + 1 == p.NW ? 0 : J + 1;
+    const int o = I * p.NW + J;
+    const float u1 = cu[o], v1 = cv[o];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const float* a = f ? cv : cu;
+        const int id = f ? p.rhs_v : p.rhs_u;
+        const float c = f ? v1 : u1;
+        float acc = 0.f;
+        if (id & 3) {
+            const float xm = a[Im * p.NW + J], xp = a[Ip * p.NW + J], ym = a[I * p.NW + Jm], yp = a[I * p.NW + Jp];
+            if (id & PPNN_RHS_ADV) {
+                const float ddx = c <= 0.f ? (-c + xp) : (c > 0.f ? (-xm + c) : 0.f);
+                const float ddy = c <= 0.f ? (-c + yp) : (c > 0.f ? (-ym + c) : 0.f);
+                acc = div_by(-u1 * ddx, p.dx, p.rdx) - div_by(v1 * ddy, p.dy, p.rdy);
+            }
+            if (id & PPNN_RHS_DIFF) {
+                const float lx = (xm + -2.f * c) + xp, ly = (ym + -2.f * c) + yp;
+                const float lap = mu * (div_by(lx, p.dx2, p.rdx2) + div_by(ly, p.dy2, p.rdy2));
+                acc = (id & PPNN_RHS_ADV) ? acc + lap : lap;
+            }
+        }
+        acc = p.dt * add_reaction(acc, id & ~3, u1, v1);
+        if (f) *out_v = acc; else *out_u = acc;
+    }
+}
+
+// dt * rhs of both fields over the whole coarse grid, by `nthr` threads
+__device__ __forceinline__ void coarse_rhs_phase(const CoarseParams& p, const float* cu, const float* cv,
+                                                 float* ru, float* rv, float mu, int tid, int nthr) {
+    const int nn2 = p.NH * p.NW;
+    if (p.adv_n == 2 && p.diff_n == 3) {
+        for (int idx = tid; idx < nn2; idx += nthr) {
+            int I = idx / p.NW, J = idx - I * p.NW;
+            eval_rhs_pair_3pt(p, cu, cv, I, J, mu, ru + idx, rv + idx);
+        }
+    } else {
+        for (int idx = tid; idx < 2 * nn2; idx += nthr) {
+            int f = idx >= nn2;
+            int r = idx - f * nn2;
+            int I = r / p.NW, J = r - I * p.NW;
+            ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);   // rv follows ru
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

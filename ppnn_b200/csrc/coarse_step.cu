@@ -100,12 +100,7 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, const StepPlan pl) {
     __syncthreads();
 
     // ---- phase 2: dt * rhs on the periodic coarse grid ----------------------
-    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
-        int f = idx >= nn2;
-        int r = idx - f * nn2;
-        int I = r / p.NW, J = r - I * p.NW;
-        ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);
-    }
+    coarse_rhs_phase(p, cu, cv, ru, rv, mu, tid, kStepThreads);
     __syncthreads();
 
     // ---- phase 3a: the duplicated-endpoint column, one point per thread -----
@@ -349,26 +344,23 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     if (pl.band_rows < 1) { pl.band_rows = p.FH; pl.nband = 1; }
     // TMA-staged path: operands through a shared-memory ring (see coarse_step_staged.cuh)
     const bool nn_ok = !io.nn || (reinterpret_cast<uintptr_t>(io.nn) & 15) == 0;
-    if (MODE != MODE_PDEU && 2 * pl.nchunk <= PPNN_STEP_WARPS && (p.FW - 1) % 4 == 0 && nn_ok && !getenv("PPNN_NO_TMA")) {
+    if (MODE != MODE_PDEU && 2 * pl.nchunk <= PPNN_STEP_WARPS && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !getenv("PPNN_NO_TMA")) {
         StagedLayout lay;
         lay.ustage = (kStageRows * p.FW + 8 + 3) & ~3;
         lay.nstage = (MODE == MODE_UPDATE && io.nn) ? kStageRows * (p.FW - 1) : 0;
-        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 3) & ~3) * sizeof(int) +
+        const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
+        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + nsteps + 3) & ~3) * sizeof(int) +
                        (size_t)((4 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
                        (size_t)kStages * 2 * (lay.ustage + lay.nstage) * sizeof(float);
         if (smem2 <= 200 * 1024) {
             const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
-            if (p.FW == 257) {
-                auto kern = coarse_step_staged_kernel<MODE, 257>;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-                if (e != cudaSuccess) return (int)e;
-                kern<<<B, kStepThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
-            } else {
-                auto kern = coarse_step_staged_kernel<MODE, 0>;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-                if (e != cudaSuccess) return (int)e;
-                kern<<<B, kStepThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
-            }
+            const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
+            void (*kern)(CoarseParams, StepIO, StepPlan, StagedLayout, const float*);
+            if (p.FW == 257) kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true> : coarse_step_staged_kernel<MODE, 257, false>;
+            else             kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<B, kStagedThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
             return launch_status();
         }
     }

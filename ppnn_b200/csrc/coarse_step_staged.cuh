@@ -56,21 +56,31 @@ struct StagedLayout {
     int nstage;      // floats per (stage, field) nn buffer: kStageRows*PW
 };
 
-template <int MODE, int FWC>
-__global__ void __launch_bounds__(kStepThreads, PPNN_MINCTA)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 producer warp
+
+// HAS_NN: the update adds the network output (MODE_UPDATE only).
+template <int MODE, int FWC, bool HAS_NN>
+__global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
                           const float* u_end) {
     extern __shared__ float4 smem4[];
     float4* roww = smem4;                                       // [FH] H-pass weights
     int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
+    int* rowadv = rowi + p.FH;                                  // [nsteps] bit q: row 8t+q moves the window on
     const int nn2 = p.NH * p.NW;
-    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 3) & ~3));
+    const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
+    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + nsteps + 3) & ~3));
     float* cv = cu + nn2;
     float* ru = cv + nn2;
     float* rv = ru + nn2;
     float* sU = cu + ((4 * nn2 + 3) & ~3);                      // [kStages][2][ustage], 16-byte aligned
     float* sN = sU + (size_t)kStages * 2 * lay.ustage;          // [kStages][2][nstage]
     __shared__ __align__(8) uint64_t full[kStages];
+    __shared__ __align__(8) uint64_t empty[kStages];
 
     const int FW = FWC ? FWC : p.FW;
     const int PW = FW - 1, PH = p.FH - 1;
@@ -81,10 +91,9 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     const size_t nplane = (size_t)PH * PW;
     const float* ub = io.u + (size_t)b * 2 * plane;
     const float mu = __ldg(io.mu + b);
-    const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
-    const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
+    const int nconsumers = min(2 * pl.nchunk, PPNN_STEP_WARPS); // warps that own a (field, chunk) column strip
 
-    // producer (thread 0): bulk copies of step t into ring slot t % kStages
+    // producer: bulk copies of step t into ring slot t % kStages (one thread)
     auto issue = [&](int t) {
         const int s = t % kStages;
         const int r0 = t * kStageRows;
@@ -108,50 +117,70 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         const int nr0 = r0 < PH ? r0 : 0;                       // the endpoint row uses network row 0 (padBC_rd)
         const int nnrows = r0 < PH ? min(kStageRows, PH - r0) : 1;
         const uint32_t nnb = (uint32_t)nnrows * PW * 4;
-        if (has_nn) total += 2 * nnb;
+        if (HAS_NN) total += 2 * nnb;
         mbar_expect_tx(&full[s], total);
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             if (nb[f]) bulk_g2s(sU + ((size_t)s * 2 + f) * lay.ustage, reinterpret_cast<const void*>(a0[f]), nb[f], &full[s]);
-            if (has_nn)
+            if (HAS_NN)
                 bulk_g2s(sN + ((size_t)s * 2 + f) * lay.nstage,
                          io.nn + ((size_t)b * 2 + f) * nplane + (size_t)nr0 * PW, nnb, &full[s]);
         }
     };
 
-    if (tid == 0) {
+    const bool producer = warp == PPNN_STEP_WARPS;
+    if (producer) {
+        if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-        fence_barrier_init();
-        for (int t = 0; t < kStages && t < nsteps; ++t) issue(t);   // in flight during phases 1 and 2
-    }
-
-    // ---- phase 1: restriction gather + row tables --------------------------
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
+            fence_barrier_init();
+            for (int t = 0; t < kStages && t < nsteps; ++t) issue(t);   // in flight during phases 1 and 2
+        }
+    } else {
+        // ---- phase 1: restriction gather + row tables (consumer warps) ----------
 #pragma unroll 4
-    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
-        int f = idx >= nn2;
-        int r = idx - f * nn2;
-        int I = r / p.NW, J = r - I * p.NW;
-        cu[idx] = restrict_point(p, ub + f * plane, I, J);
-    }
-    for (int i = tid; i < p.FH; i += kStepThreads) {
-        float w[4]; int i0;
-        cubic_entry(p.suh, i, &i0, w);
-        rowi[i] = i0;
-        roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+        for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
+            int f = idx >= nn2;
+            int r = idx - f * nn2;
+            int I = r / p.NW, J = r - I * p.NW;
+            cu[idx] = restrict_point(p, ub + f * plane, I, J);
+        }
+        for (int i = tid; i < p.FH; i += kStepThreads) {
+            float w[4]; int i0;
+            cubic_entry(p.suh, i, &i0, w);
+            rowi[i] = i0;
+            roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+        }
+        for (int t = tid; t < nsteps; t += kStepThreads) {
+            int bits = 0;
+            for (int q = 0; q < kStageRows; ++q) {
+                const int i = t * kStageRows + q;
+                if (i > 0 && i < p.FH && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
+            }
+            rowadv[t] = bits;
+        }
     }
     __syncthreads();
 
-    // ---- phase 2: dt * rhs on the periodic coarse grid ----------------------
-    for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
-        int f = idx >= nn2;
-        int r = idx - f * nn2;
-        int I = r / p.NW, J = r - I * p.NW;
-        ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);
+    // ---- phase 2: dt * rhs on the periodic coarse grid --------------------------
+    if (!producer) {
+        coarse_rhs_phase(p, cu, cv, ru, rv, mu, tid, kStepThreads);
     }
     __syncthreads();
 
-    // ---- phase 3a: the duplicated-endpoint column, one point per thread -----
+    if (producer) {
+        // ---- producer warp: refill a slot as soon as every consumer warp released it ----
+        if (lane == 0) {
+            for (int t = kStages; t < nsteps; ++t) {
+                mbar_wait(&empty[t % kStages], ((t / kStages) - 1) & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t);
+            }
+        }
+        return;
+    }
+
+    // ---- phase 3a: the duplicated-endpoint column, one point per thread --------
     const bool want_out = MODE == MODE_INPUTS ? io.out != nullptr : true;
     if (pl.wmain < FW && want_out) {
         const int jc = FW - 1;
@@ -176,7 +205,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
             if (MODE == MODE_UPDATE) {
                 const float uu = ld_stream(io.u + o);
                 float v = uu + pde;
-                if (has_nn) {
+                if (HAS_NN) {
                     const float n = ld_stream(io.nn + ((size_t)b * 2 + f) * nplane + (size_t)(i == PH ? 0 : i) * PW);
                     v = (n * (f ? io.s0[1] : io.s0[0]) + (f ? io.m0[1] : io.m0[0])) + uu + pde;
                 }
@@ -188,14 +217,14 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     }
 
     // ---- phase 3b: warp = (field, 32-column chunk), all rows, operands from the ring --
+    if (warp >= nconsumers) return;
     const int f = warp / pl.nchunk;
     const int chunk = warp - f * pl.nchunk;
-    const bool mine = f < 2;                                    // spare warps only keep the barriers company
     const int j = chunk * 32 + lane;
-    const bool active = mine && j < pl.wmain;
-    const int jc = j < pl.wmain ? j : pl.wmain - 1;
+    const bool active = j < pl.wmain;
+    const int jc = active ? j : pl.wmain - 1;
     const int jn = jc == PW ? 0 : jc;                           // padBC_rd column fold
-    const float* rf = (f & 1) ? rv : ru;
+    const float* rf = f ? rv : ru;
 
     float wy[4]; int j0;
     cubic_entry(p.suw, jc, &j0, wy);
@@ -203,67 +232,78 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     const float* rc1 = rf + ext_index(j0, p.CW);
     const float* rc2 = rf + ext_index(j0 + 1, p.CW);
     const float* rc3 = rf + ext_index(j0 + 2, p.CW);
-    auto yrow = [&](int I) -> float {
+    auto yrow = [&](int I) -> float {                           // W pass of row I of the extended increment
         const int o = ext_index(I, p.CH) * p.NW;
         return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
     };
     int base = rowi[0];
     float h0 = yrow(base - 1), h1 = yrow(base), h2 = yrow(base + 1), h3 = yrow(base + 2);
-    auto prolong = [&](int ii) -> float {
-        const int i0 = rowi[ii];
-        const float4 wx = roww[ii];
-        if (i0 != base) {
-            if (i0 == base + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = yrow(i0 + 2); }
-            else { h0 = yrow(i0 - 1); h1 = yrow(i0); h2 = yrow(i0 + 1); h3 = yrow(i0 + 2); }
-            base = i0;
-        }
+    // H pass of one fine row; prolongation never skips a coarse row (F >= C), so the
+    // window moves on by at most one row (flag from the per-band bit mask; warp-uniform)
+    auto prolong = [&](const float4 wx, bool adv) -> float {
+        if (adv) { ++base; h0 = h1; h1 = h2; h2 = h3; h3 = yrow(base + 2); }
         return h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w;
     };
 
-    const int fc = mine ? f : 0;
-    const float m0 = fc ? io.m0[1] : io.m0[0], s0 = fc ? io.s0[1] : io.s0[0];
-    const float m1 = fc ? io.m1[1] : io.m1[0], s1 = fc ? io.s1[1] : io.s1[0];
+    const float m0 = f ? io.m0[1] : io.m0[0], s0 = f ? io.s0[1] : io.s0[0];
+    const float m1 = f ? io.m1[1] : io.m1[0], s1 = f ? io.s1[1] : io.s1[0];
     const float rs0 = 1.f / s0, rs1 = 1.f / s1;
-    const size_t foff = ((size_t)b * 2 + fc) * plane + jc;
-    const size_t noff = ((size_t)b * 2 + fc) * nplane + jc;
-    float* op = io.out ? io.out + foff : nullptr;
-    float* unp = MODE == MODE_INPUTS ? io.u_norm + noff : nullptr;
-    float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + noff : nullptr;
+    float* op = io.out ? io.out + ((size_t)b * 2 + f) * plane + jc : nullptr;
+    float* unp = MODE == MODE_INPUTS ? io.u_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
+    float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
     const bool colok = active && jc < PW;
+    // kStageRows * FW * 4 is a multiple of 16, so the lead of every band of this plane is the same
+    const int lead = (int)(reinterpret_cast<uintptr_t>(ub + f * plane) & 15) >> 2;
+    const float* su_base = sU + (size_t)f * lay.ustage + lead + jc;
+    const float* sn_base = sN + (size_t)f * lay.nstage + jn;
+    const float4* wrow = roww;
+
+    auto row_out = [&](int q, int row, int advbits, const float* su, const float* sn) {
+        const float pde = prolong(wrow[q], (advbits >> q) & 1);
+        const float uu = su[q * FW];
+        if (MODE == MODE_UPDATE) {
+            const float v = HAS_NN ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
+            if (active) st_stream(op + (size_t)q * FW, v);
+        } else {
+            if (op && active) st_stream(op + (size_t)q * FW, pde);
+            if (colok && row < PH) {
+                st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
+                if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
+            }
+        }
+    };
 
     for (int t = 0; t < nsteps; ++t) {
         const int s = t % kStages;
         const int r0 = t * kStageRows;
+        const float* su = su_base + (size_t)s * 2 * lay.ustage;
+        const float* sn = sn_base + (size_t)s * 2 * lay.nstage;
+        const int advbits = rowadv[t];
         mbar_wait(&full[s], (t / kStages) & 1);
-        if (mine) {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(ub + fc * plane + (size_t)r0 * FW);
-            const int lead = (int)(a & 15) >> 2;
-            const float* su = sU + ((size_t)s * 2 + fc) * lay.ustage + lead + jc;
-            const float* sn = sN + ((size_t)s * 2 + fc) * lay.nstage + jn;
+        if (r0 + kStageRows <= p.FH) {
 #pragma unroll
-            for (int q = 0; q < kStageRows; ++q) {
-                const int row = r0 + q;
-                if (row < p.FH) {                               // warp-uniform
-                    const float pde = prolong(row);
-                    const float uu = su[q * FW];
-                    if (MODE == MODE_UPDATE) {
-                        const float v = has_nn ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
-                        if (active) st_stream(op + (size_t)row * FW, v);
-                    } else {
-                        if (op && active) st_stream(op + (size_t)row * FW, pde);
-                        if (colok && row < PH) {
-                            st_stream(unp + (size_t)row * PW, div_by(uu - m0, s0, rs0));
-                            if (pnp) st_stream(pnp + (size_t)row * PW, div_by(pde - m1, s1, rs1));
-                        }
+            for (int q = 0; q < kStageRows; ++q) row_out(q, r0 + q, advbits, su, sn);
+        } else {
+            for (int q = 0; r0 + q < p.FH; ++q) {               // ragged last band (the endpoint row)
+                const float pde = prolong(wrow[q], (advbits >> q) & 1);
+                const float uu = su[q * FW];
+                if (MODE == MODE_UPDATE) {
+                    const float v = HAS_NN ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
+                    if (active) st_stream(op + (size_t)q * FW, v);
+                } else {
+                    if (op && active) st_stream(op + (size_t)q * FW, pde);
+                    if (colok && r0 + q < PH) {
+                        st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
+                        if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
                     }
                 }
             }
         }
-        __syncthreads();                                        // slot s is free again
-        if (tid == 0 && t + kStages < nsteps) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(t + kStages);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);                  // this warp is done with slot s
+        wrow += kStageRows;
+        if (op) op += (size_t)kStageRows * FW;
+        if (MODE == MODE_INPUTS) { unp += (size_t)kStageRows * PW; if (pnp) pnp += (size_t)kStageRows * PW; }
     }
 }
 

@@ -136,7 +136,8 @@ int ppnn_step_inputs(const ppnn_coarse_cfg* cfg, const float* u, const float* mu
 /* The explicit update of one rollout step (src/train2D.py:235-238), fused with
  * pde_du:  u_next = padBC_rd(nn_out*outstd + outmean) + u + pde_du(u, mu).
  * nn_out [B,2,FH-1,FW-1] may be NULL: u_next = u + pde_du(u)  (the PDE-only
- * rollout of post_process/test_predict_2Dp.py:116).  u_next may alias u.        */
+ * rollout of post_process/test_predict_2Dp.py:116).  u_next must NOT overlap u
+ * (the two field planes of a sample are processed by different CTAs).            */
 int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                      const float* nn_out, const float* outmean, const float* outstd,
                      float* u_next, int B, void* stream);

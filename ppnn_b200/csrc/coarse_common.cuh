@@ -181,6 +181,31 @@ __device__ __forceinline__ void eval_rhs_pair_3pt(const CoarseParams& p, const f
     }
 }
 
+// dt * rhs of ONE field at one coarse point, same 3-point fast path
+__device__ __forceinline__ float eval_rhs_3pt(const CoarseParams& p, int id, const float* a,
+                                              const float* cu, const float* cv, int I, int J, float mu) {
+    const int o = I * p.NW + J;
+    const float u1 = cu[o], v1 = cv[o];
+    float acc = 0.f;
+    if (id & 3) {
+        const int Im = (I == 0 ? p.NH : I) - 1, Ip = I + 1 == p.NH ? 0 : I + 1;
+        const int Jm = (J == 0 ? p.NW : J) - 1, Jp = J + 1 == p.NW ? 0 : J + 1;
+        const float c = a[o];
+        const float xm = a[Im * p.NW + J], xp = a[Ip * p.NW + J], ym = a[I * p.NW + Jm], yp = a[I * p.NW + Jp];
+        if (id & PPNN_RHS_ADV) {
+            const float ddx = c <= 0.f ? (-c + xp) : (c > 0.f ? (-xm + c) : 0.f);
+            const float ddy = c <= 0.f ? (-c + yp) : (c > 0.f ? (-ym + c) : 0.f);
+            acc = div_by(-u1 * ddx, p.dx, p.rdx) - div_by(v1 * ddy, p.dy, p.rdy);
+        }
+        if (id & PPNN_RHS_DIFF) {
+            const float lx = (xm + -2.f * c) + xp, ly = (ym + -2.f * c) + yp;
+            const float lap = mu * (div_by(lx, p.dx2, p.rdx2) + div_by(ly, p.dy2, p.rdy2));
+            acc = (id & PPNN_RHS_ADV) ? acc + lap : lap;
+        }
+    }
+    return p.dt * add_reaction(acc, id & ~3, u1, v1);
+}
+
 // dt * rhs of both fields over the whole coarse grid, by `nthr` threads
 __device__ __forceinline__ void coarse_rhs_phase(const CoarseParams& p, const float* cu, const float* cv,
                                                  float* ru, float* rv, float mu, int tid, int nthr) {

@@ -344,13 +344,21 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     if (pl.band_rows < 1) { pl.band_rows = p.FH; pl.nband = 1; }
     // TMA-staged path: operands through a shared-memory ring (see coarse_step_staged.cuh)
     const bool nn_ok = !io.nn || (reinterpret_cast<uintptr_t>(io.nn) & 15) == 0;
-    if (MODE != MODE_PDEU && 2 * pl.nchunk <= PPNN_STEP_WARPS && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !getenv("PPNN_NO_TMA")) {
+    if (MODE != MODE_PDEU && pl.nchunk <= PPNN_STEP_WARPS && B < (1 << 30) && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !getenv("PPNN_NO_TMA")) {
         StagedLayout lay;
         lay.ustage = (kStageRows * p.FW + 8 + 3) & ~3;
         lay.nstage = (MODE == MODE_UPDATE && io.nn) ? kStageRows * (p.FW - 1) : 0;
-        const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
-        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + nsteps + 3) & ~3) * sizeof(int) +
-                       (size_t)((4 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
+        // two row groups of 8 chunks each when the mesh is narrow enough for both to fit the CTA
+        lay.split = p.FH;
+        if (2 * pl.nchunk <= PPNN_STEP_WARPS && p.FH >= 4 * kStageRows)
+            lay.split = ((p.FH / 2 + kStageRows - 1) / kStageRows) * kStageRows;
+        {
+            int n0 = (lay.split + kStageRows - 1) / kStageRows;
+            int n1 = (p.FH - lay.split + kStageRows - 1) / kStageRows;
+            lay.nsteps = n0 > n1 ? n0 : n1;
+        }
+        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + 3) & ~3) * sizeof(int) +
+                       (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
                        (size_t)kStages * 2 * (lay.ustage + lay.nstage) * sizeof(float);
         if (smem2 <= 200 * 1024) {
             const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
@@ -360,7 +368,7 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
             else             kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
-            kern<<<B, kStagedThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
+            kern<<<2 * B, kStagedThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
             return launch_status();
         }
     }
@@ -400,6 +408,7 @@ extern "C" int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, cons
                                 float* u_next, int B, void* stream) {
     if (!u || !mu || !u_next) return PPNN_E_NULL;
     if (nn_out && (!outmean || !outstd)) return PPNN_E_NULL;
+    if (u_next == u) return PPNN_E_MODE;      // planes of one sample run on different CTAs: no in-place update
     StepIO io = {};
     io.u = u; io.mu = mu; io.nn = nn_out; io.out = u_next;
     for (int c = 0; c < 2; ++c) { io.m0[c] = nn_out ? outmean[c] : 0.f; io.s0[c] = nn_out ? outstd[c] : 1.f; }

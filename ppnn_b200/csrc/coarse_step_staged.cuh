@@ -21,8 +21,14 @@
 
 namespace ppnn {
 
-constexpr int kStageRows = 8;
-constexpr int kStages = 2;
+#ifndef PPNN_STAGE_ROWS
+#define PPNN_STAGE_ROWS 4
+#endif
+#ifndef PPNN_STAGES
+#define PPNN_STAGES 4
+#endif
+constexpr int kStageRows = PPNN_STAGE_ROWS;   // kStageRows * FW must be a multiple of 4 (constant lead)
+constexpr int kStages = PPNN_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -52,8 +58,10 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 
 struct StagedLayout {
-    int ustage;      // floats per (stage, field) u buffer: kStageRows*FW + 8 (lead / tail slack), 16 B multiple
-    int nstage;      // floats per (stage, field) nn buffer: kStageRows*PW
+    int ustage;      // floats per (stage, group) u buffer: kStageRows*FW + 8 (lead / tail slack), 16 B multiple
+    int nstage;      // floats per (stage, group) nn buffer: kStageRows*PW
+    int split;       // first row of the second warp group (multiple of kStageRows); FH = no second group
+    int nsteps;      // ring steps = max over groups of ceil(rows / kStageRows)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -61,8 +69,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 producer warp
+constexpr int kGatherBatch = 5;                     // coarse points per thread whose loads are issued together
 
-// HAS_NN: the update adds the network output (MODE_UPDATE only).
+// One CTA = one (sample, field) plane.  Consumer warp = (row group g, 32-column
+// chunk): group 0 walks rows [0, split), group 1 rows [split, FH), both fed by
+// the same ring step.  HAS_NN: the update adds the network output (MODE_UPDATE).
 template <int MODE, int FWC, bool HAS_NN>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
@@ -70,61 +81,61 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     extern __shared__ float4 smem4[];
     float4* roww = smem4;                                       // [FH] H-pass weights
     int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
-    int* rowadv = rowi + p.FH;                                  // [nsteps] bit q: row 8t+q moves the window on
+    int* rowadv = rowi + p.FH;                                  // [2][nsteps] bit q: row rs_g + R*t + q moves the window
     const int nn2 = p.NH * p.NW;
-    const int nsteps = (p.FH + kStageRows - 1) / kStageRows;
-    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + nsteps + 3) & ~3));
+    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 2 * lay.nsteps + 3) & ~3));
     float* cv = cu + nn2;
-    float* ru = cv + nn2;
-    float* rv = ru + nn2;
-    float* sU = cu + ((4 * nn2 + 3) & ~3);                      // [kStages][2][ustage], 16-byte aligned
+    float* rf = cv + nn2;                                       // dt * rhs of this CTA's field
+    float* sU = cu + ((3 * nn2 + 3) & ~3);                      // [kStages][2][ustage], 16-byte aligned
     float* sN = sU + (size_t)kStages * 2 * lay.ustage;          // [kStages][2][nstage]
     __shared__ __align__(8) uint64_t full[kStages];
     __shared__ __align__(8) uint64_t empty[kStages];
 
     const int FW = FWC ? FWC : p.FW;
     const int PW = FW - 1, PH = p.FH - 1;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x >> 1, f = blockIdx.x & 1;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const size_t plane = (size_t)p.FH * FW;
     const size_t nplane = (size_t)PH * PW;
-    const float* ub = io.u + (size_t)b * 2 * plane;
+    const float* ub = io.u + (size_t)b * 2 * plane;             // both fields of the sample (gather)
+    const float* uf = ub + f * plane;                           // this CTA's plane
+    const float* nf = HAS_NN ? io.nn + ((size_t)b * 2 + f) * nplane : nullptr;
     const float mu = __ldg(io.mu + b);
-    const int nconsumers = min(2 * pl.nchunk, PPNN_STEP_WARPS); // warps that own a (field, chunk) column strip
+    const int ngroups = lay.split < p.FH ? 2 : 1;
+    const int nconsumers = min(ngroups * pl.nchunk, PPNN_STEP_WARPS);
+    const int rid = f ? p.rhs_v : p.rhs_u;
 
-    // producer: bulk copies of step t into ring slot t % kStages (one thread)
+    // producer: bulk copies of ring step t (kStageRows rows of each row group) into slot t % kStages
     auto issue = [&](int t) {
         const int s = t % kStages;
-        const int r0 = t * kStageRows;
-        const int nrows = min(kStageRows, p.FH - r0);
-        uintptr_t a0[2]; uint32_t nb[2]; uint32_t total = 0;
+        uintptr_t a0[2]; uint32_t nb[2] = {0, 0}, nnb[2] = {0, 0}; int nr0[2] = {0, 0};
+        uint32_t total = 0;
         const uintptr_t end_al = reinterpret_cast<uintptr_t>(u_end) & ~(uintptr_t)15;
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(ub + f * plane + (size_t)r0 * FW);
-            a0[f] = a & ~(uintptr_t)15;
-            nb[f] = (uint32_t)((a - a0[f]) + (size_t)nrows * FW * 4 + 15) & ~15u;
-            if (a0[f] + nb[f] > end_al) {                       // last copy of the tensor: stay inside it
-                const uint32_t inside = (uint32_t)(end_al - a0[f]);
-                float* dst = sU + ((size_t)s * 2 + f) * lay.ustage;
+        for (int g = 0; g < 2; ++g) {
+            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
+            const int r0 = rs + t * kStageRows;
+            if (g >= ngroups || r0 >= re) continue;
+            const int nrows = min(kStageRows, re - r0);
+            const uintptr_t a = reinterpret_cast<uintptr_t>(uf + (size_t)r0 * FW);
+            a0[g] = a & ~(uintptr_t)15;
+            nb[g] = (uint32_t)((a - a0[g]) + (size_t)nrows * FW * 4 + 15) & ~15u;
+            if (a0[g] + nb[g] > end_al) {                       // last copy of the tensor: stay inside it
+                float* dst = sU + ((size_t)s * 2 + g) * lay.ustage;
                 for (const float* q = reinterpret_cast<const float*>(end_al); q < u_end; ++q)
-                    dst[(reinterpret_cast<uintptr_t>(q) - a0[f]) >> 2] = *q;
-                nb[f] = inside;
+                    dst[(reinterpret_cast<uintptr_t>(q) - a0[g]) >> 2] = *q;
+                nb[g] = (uint32_t)(end_al - a0[g]);
             }
-            total += nb[f];
+            nr0[g] = r0 < PH ? r0 : 0;                          // the endpoint row uses network row 0 (padBC_rd)
+            nnb[g] = HAS_NN ? (uint32_t)(r0 < PH ? min(kStageRows, PH - r0) : 1) * PW * 4 : 0;
+            total += nb[g] + nnb[g];
         }
-        const int nr0 = r0 < PH ? r0 : 0;                       // the endpoint row uses network row 0 (padBC_rd)
-        const int nnrows = r0 < PH ? min(kStageRows, PH - r0) : 1;
-        const uint32_t nnb = (uint32_t)nnrows * PW * 4;
-        if (HAS_NN) total += 2 * nnb;
         mbar_expect_tx(&full[s], total);
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            if (nb[f]) bulk_g2s(sU + ((size_t)s * 2 + f) * lay.ustage, reinterpret_cast<const void*>(a0[f]), nb[f], &full[s]);
-            if (HAS_NN)
-                bulk_g2s(sN + ((size_t)s * 2 + f) * lay.nstage,
-                         io.nn + ((size_t)b * 2 + f) * nplane + (size_t)nr0 * PW, nnb, &full[s]);
+        for (int g = 0; g < 2; ++g) {
+            if (nb[g]) bulk_g2s(sU + ((size_t)s * 2 + g) * lay.ustage, reinterpret_cast<const void*>(a0[g]), nb[g], &full[s]);
+            if (nnb[g]) bulk_g2s(sN + ((size_t)s * 2 + g) * lay.nstage, nf + (size_t)nr0[g] * PW, nnb[g], &full[s]);
         }
     };
 
@@ -134,16 +145,44 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
 #pragma unroll
             for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
             fence_barrier_init();
-            for (int t = 0; t < kStages && t < nsteps; ++t) issue(t);   // in flight during phases 1 and 2
+            for (int t = 0; t < kStages && t < lay.nsteps; ++t) issue(t);   // in flight during phases 1 and 2
         }
     } else {
-        // ---- phase 1: restriction gather + row tables (consumer warps) ----------
-#pragma unroll 4
-        for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) {
-            int f = idx >= nn2;
-            int r = idx - f * nn2;
-            int I = r / p.NW, J = r - I * p.NW;
-            cu[idx] = restrict_point(p, ub + f * plane, I, J);
+        // ---- phase 1: restriction gather (loads of kGatherBatch points in flight) + row tables ----
+        // a purely diffusive right-hand side never reads the other field
+        const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
+        const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
+        for (int i0 = lo + tid; i0 < hi; i0 += kGatherBatch * kStepThreads) {
+            float a[kGatherBatch], bq[kGatherBatch], c[kGatherBatch], d[kGatherBatch];
+            BilinearTap tp[kGatherBatch];
+#pragma unroll
+            for (int k = 0; k < kGatherBatch; ++k) {
+                const int idx = i0 + k * kStepThreads;
+                a[k] = bq[k] = c[k] = d[k] = 0.f;
+                if (idx < hi) {
+                    const int g = idx >= nn2;
+                    const int r = idx - g * nn2;
+                    const int I = r / p.NW, J = r - I * p.NW;
+                    tp[k] = bilinear_tap(p, I, J);
+                    const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
+                    a[k] = __ldg(q);
+                    if (tp[k].lj != 0.f) bq[k] = __ldg(q + tp[k].dj);
+                    if (tp[k].li != 0.f) {
+                        const float* r2 = q + (size_t)tp[k].di * FW;
+                        c[k] = __ldg(r2);
+                        if (tp[k].lj != 0.f) d[k] = __ldg(r2 + tp[k].dj);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kGatherBatch; ++k) {
+                const int idx = i0 + k * kStepThreads;
+                if (idx < hi) {
+                    const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
+                    const float top = w0 * a[k] + tp[k].lj * bq[k];
+                    cu[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * c[k] + tp[k].lj * d[k]);
+                }
+            }
         }
         for (int i = tid; i < p.FH; i += kStepThreads) {
             float w[4]; int i0;
@@ -151,27 +190,39 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
             rowi[i] = i0;
             roww[i] = make_float4(w[0], w[1], w[2], w[3]);
         }
-        for (int t = tid; t < nsteps; t += kStepThreads) {
+        for (int e = tid; e < 2 * lay.nsteps; e += kStepThreads) {
+            const int g = e >= lay.nsteps, t = e - g * lay.nsteps;
+            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
             int bits = 0;
             for (int q = 0; q < kStageRows; ++q) {
-                const int i = t * kStageRows + q;
-                if (i > 0 && i < p.FH && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
+                const int i = rs + t * kStageRows + q;
+                if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
             }
-            rowadv[t] = bits;
+            rowadv[e] = bits;
         }
     }
     __syncthreads();
 
-    // ---- phase 2: dt * rhs on the periodic coarse grid --------------------------
+    // ---- phase 2: dt * rhs of this CTA's field on the periodic coarse grid ------
     if (!producer) {
-        coarse_rhs_phase(p, cu, cv, ru, rv, mu, tid, kStepThreads);
+        if (p.adv_n == 2 && p.diff_n == 3) {
+            for (int idx = tid; idx < nn2; idx += kStepThreads) {
+                const int I = idx / p.NW, J = idx - I * p.NW;
+                rf[idx] = eval_rhs_3pt(p, rid, f ? cv : cu, cu, cv, I, J, mu);
+            }
+        } else {
+            for (int idx = tid; idx < nn2; idx += kStepThreads) {
+                const int I = idx / p.NW, J = idx - I * p.NW;
+                rf[idx] = p.dt * eval_rhs(p, rid, f ? cv : cu, cu, cv, I, J, mu);
+            }
+        }
     }
     __syncthreads();
 
     if (producer) {
         // ---- producer warp: refill a slot as soon as every consumer warp released it ----
         if (lane == 0) {
-            for (int t = kStages; t < nsteps; ++t) {
+            for (int t = kStages; t < lay.nsteps; ++t) {
                 mbar_wait(&empty[t % kStages], ((t / kStages) - 1) & 1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(t);
@@ -179,6 +230,9 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         }
         return;
     }
+
+    const float m0 = f ? io.m0[1] : io.m0[0], s0 = f ? io.s0[1] : io.s0[0];
+    const float m1 = f ? io.m1[1] : io.m1[0], s1 = f ? io.s1[1] : io.s1[0];
 
     // ---- phase 3a: the duplicated-endpoint column, one point per thread --------
     const bool want_out = MODE == MODE_INPUTS ? io.out != nullptr : true;
@@ -188,10 +242,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         cubic_entry(p.suw, jc, &j0, wy);
         const int c0 = ext_index(j0 - 1, p.CW), c1 = ext_index(j0, p.CW),
                   c2 = ext_index(j0 + 1, p.CW), c3 = ext_index(j0 + 2, p.CW);
-        for (int idx = tid; idx < 2 * p.FH; idx += kStepThreads) {
-            const int f = idx >= p.FH;
-            const int i = idx - f * p.FH;
-            const float* rf = f ? rv : ru;
+        for (int i = tid; i < p.FH; i += kStepThreads) {
             const int i0 = rowi[i];
             const float4 wx = roww[i];
             float h[4];
@@ -205,10 +256,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
             if (MODE == MODE_UPDATE) {
                 const float uu = ld_stream(io.u + o);
                 float v = uu + pde;
-                if (HAS_NN) {
-                    const float n = ld_stream(io.nn + ((size_t)b * 2 + f) * nplane + (size_t)(i == PH ? 0 : i) * PW);
-                    v = (n * (f ? io.s0[1] : io.s0[0]) + (f ? io.m0[1] : io.m0[0])) + uu + pde;
-                }
+                if (HAS_NN) v = (ld_stream(nf + (size_t)(i == PH ? 0 : i) * PW) * s0 + m0) + uu + pde;
                 st_stream(io.out + o, v);
             } else {
                 st_stream(io.out + o, pde);
@@ -216,15 +264,15 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         }
     }
 
-    // ---- phase 3b: warp = (field, 32-column chunk), all rows, operands from the ring --
+    // ---- phase 3b: warp = (row group, 32-column chunk), operands from the ring ----
     if (warp >= nconsumers) return;
-    const int f = warp / pl.nchunk;
-    const int chunk = warp - f * pl.nchunk;
+    const int g = warp / pl.nchunk;
+    const int chunk = warp - g * pl.nchunk;
+    const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
     const int j = chunk * 32 + lane;
     const bool active = j < pl.wmain;
     const int jc = active ? j : pl.wmain - 1;
     const int jn = jc == PW ? 0 : jc;                           // padBC_rd column fold
-    const float* rf = f ? rv : ru;
 
     float wy[4]; int j0;
     cubic_entry(p.suw, jc, &j0, wy);
@@ -236,7 +284,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         const int o = ext_index(I, p.CH) * p.NW;
         return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
     };
-    int base = rowi[0];
+    int base = rowi[rs];
     float h0 = yrow(base - 1), h1 = yrow(base), h2 = yrow(base + 1), h3 = yrow(base + 2);
     // H pass of one fine row; prolongation never skips a coarse row (F >= C), so the
     // window moves on by at most one row (flag from the per-band bit mask; warp-uniform)
@@ -245,18 +293,17 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         return h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w;
     };
 
-    const float m0 = f ? io.m0[1] : io.m0[0], s0 = f ? io.s0[1] : io.s0[0];
-    const float m1 = f ? io.m1[1] : io.m1[0], s1 = f ? io.s1[1] : io.s1[0];
     const float rs0 = 1.f / s0, rs1 = 1.f / s1;
-    float* op = io.out ? io.out + ((size_t)b * 2 + f) * plane + jc : nullptr;
-    float* unp = MODE == MODE_INPUTS ? io.u_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
-    float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + ((size_t)b * 2 + f) * nplane + jc : nullptr;
+    float* op = io.out ? io.out + ((size_t)b * 2 + f) * plane + (size_t)rs * FW + jc : nullptr;
+    float* unp = MODE == MODE_INPUTS ? io.u_norm + ((size_t)b * 2 + f) * nplane + (size_t)rs * PW + jc : nullptr;
+    float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + ((size_t)b * 2 + f) * nplane + (size_t)rs * PW + jc : nullptr;
     const bool colok = active && jc < PW;
-    // kStageRows * FW * 4 is a multiple of 16, so the lead of every band of this plane is the same
-    const int lead = (int)(reinterpret_cast<uintptr_t>(ub + f * plane) & 15) >> 2;
-    const float* su_base = sU + (size_t)f * lay.ustage + lead + jc;
-    const float* sn_base = sN + (size_t)f * lay.nstage + jn;
-    const float4* wrow = roww;
+    // kStageRows * FW and split * FW are multiples of 4 floats, so every band of this plane has the same lead
+    const int lead = (int)(reinterpret_cast<uintptr_t>(uf) & 15) >> 2;
+    const float* su_base = sU + (size_t)g * lay.ustage + lead + jc;
+    const float* sn_base = sN + (size_t)g * lay.nstage + jn;
+    const float4* wrow = roww + rs;
+    const int* advp = rowadv + g * lay.nsteps;
 
     auto row_out = [&](int q, int row, int advbits, const float* su, const float* sn) {
         const float pde = prolong(wrow[q], (advbits >> q) & 1);
@@ -273,31 +320,18 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         }
     };
 
-    for (int t = 0; t < nsteps; ++t) {
+    for (int t = 0; t < lay.nsteps; ++t) {
         const int s = t % kStages;
-        const int r0 = t * kStageRows;
+        const int r0 = rs + t * kStageRows;
         const float* su = su_base + (size_t)s * 2 * lay.ustage;
         const float* sn = sn_base + (size_t)s * 2 * lay.nstage;
-        const int advbits = rowadv[t];
+        const int advbits = advp[t];
         mbar_wait(&full[s], (t / kStages) & 1);
-        if (r0 + kStageRows <= p.FH) {
+        if (r0 + kStageRows <= re) {
 #pragma unroll
             for (int q = 0; q < kStageRows; ++q) row_out(q, r0 + q, advbits, su, sn);
         } else {
-            for (int q = 0; r0 + q < p.FH; ++q) {               // ragged last band (the endpoint row)
-                const float pde = prolong(wrow[q], (advbits >> q) & 1);
-                const float uu = su[q * FW];
-                if (MODE == MODE_UPDATE) {
-                    const float v = HAS_NN ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
-                    if (active) st_stream(op + (size_t)q * FW, v);
-                } else {
-                    if (op && active) st_stream(op + (size_t)q * FW, pde);
-                    if (colok && r0 + q < PH) {
-                        st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
-                        if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
-                    }
-                }
-            }
+            for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sn);   // ragged last band
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);                  // this warp is done with slot s

@@ -188,7 +188,7 @@ class CoarseStep:
         return _StepUpdateFn.apply(u, mu, nn_out, self, outmean, outstd)
 
     def step_update_(self, u, mu, nn_out, outmean2, outstd2, out) -> torch.Tensor:
-        """Allocation-free, autograd-free update into ``out`` (may alias ``u``); the
+        """Allocation-free, autograd-free update into ``out`` (must not overlap ``u``); the
         statistics are pre-converted ``float[2]`` arrays (``_lib.f2``) -- for graphs."""
         lib = L.load()
         B = u.shape[0]

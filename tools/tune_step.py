@@ -35,7 +35,7 @@ res["pde_du"] = t(lambda: step.pde_du(u, mu))
 print(json.dumps(res))
 ''' % ROOT
 for lib in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so"))):
-    for extra in ({}, {"PPNN_NO_TMA": "1"}):
+    for extra in ({},):
         env = dict(os.environ, PPNN_B200_LIB=lib, **extra)
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-600:]

@@ -52,6 +52,43 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 eviction-priority policies: the restriction gather touches sectors that the
+// TMA stream re-reads tens of microseconds later -> keep them (evict_last); the
+// streamed bands themselves are dead after one use (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#ifndef PPNN_HINT_GATHER
+#define PPNN_HINT_GATHER 1
+#endif
+#ifndef PPNN_HINT_STREAM
+#define PPNN_HINT_STREAM 0
+#endif
+__device__ __forceinline__ float ld_hint(const float* p, uint64_t pol) {
+#if PPNN_HINT_GATHER
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+#if !PPNN_HINT_STREAM
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    return;
+#endif
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -106,6 +143,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     const int nconsumers = min(ngroups * pl.nchunk, PPNN_STEP_WARPS);
     const int rid = f ? p.rhs_v : p.rhs_u;
 
+    const uint64_t pol_stream = l2_policy_evict_first();
     // producer: bulk copies of ring step t (kStageRows rows of each row group) into slot t % kStages
     auto issue = [&](int t) {
         const int s = t % kStages;
@@ -134,14 +172,14 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         mbar_expect_tx(&full[s], total);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            if (nb[g]) bulk_g2s(sU + ((size_t)s * 2 + g) * lay.ustage, reinterpret_cast<const void*>(a0[g]), nb[g], &full[s]);
-            if (nnb[g]) bulk_g2s(sN + ((size_t)s * 2 + g) * lay.nstage, nf + (size_t)nr0[g] * PW, nnb[g], &full[s]);
+            if (nb[g]) bulk_g2s_hint(sU + ((size_t)s * 2 + g) * lay.ustage, reinterpret_cast<const void*>(a0[g]), nb[g], &full[s], pol_stream);
+            if (nnb[g]) bulk_g2s_hint(sN + ((size_t)s * 2 + g) * lay.nstage, nf + (size_t)nr0[g] * PW, nnb[g], &full[s], pol_stream);
         }
     };
 
     const bool producer = warp == PPNN_STEP_WARPS;
     if (producer) {
-        if (lane == 0) {
+        if (lane == 0 && MODE != MODE_PDEU) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
             fence_barrier_init();
@@ -152,6 +190,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         // a purely diffusive right-hand side never reads the other field
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
+        const uint64_t pol_keep = l2_policy_evict_last();
         for (int i0 = lo + tid; i0 < hi; i0 += kGatherBatch * kStepThreads) {
             float a[kGatherBatch], bq[kGatherBatch], c[kGatherBatch], d[kGatherBatch];
             BilinearTap tp[kGatherBatch];
@@ -165,12 +204,12 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
                     const int I = r / p.NW, J = r - I * p.NW;
                     tp[k] = bilinear_tap(p, I, J);
                     const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
-                    a[k] = __ldg(q);
-                    if (tp[k].lj != 0.f) bq[k] = __ldg(q + tp[k].dj);
+                    a[k] = ld_hint(q, pol_keep);
+                    if (tp[k].lj != 0.f) bq[k] = ld_hint(q + tp[k].dj, pol_keep);
                     if (tp[k].li != 0.f) {
                         const float* r2 = q + (size_t)tp[k].di * FW;
-                        c[k] = __ldg(r2);
-                        if (tp[k].lj != 0.f) d[k] = __ldg(r2 + tp[k].dj);
+                        c[k] = ld_hint(r2, pol_keep);
+                        if (tp[k].lj != 0.f) d[k] = ld_hint(r2 + tp[k].dj, pol_keep);
                     }
                 }
             }
@@ -221,7 +260,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
 
     if (producer) {
         // ---- producer warp: refill a slot as soon as every consumer warp released it ----
-        if (lane == 0) {
+        if (lane == 0 && MODE != MODE_PDEU) {
             for (int t = kStages; t < lay.nsteps; ++t) {
                 mbar_wait(&empty[t % kStages], ((t / kStages) - 1) & 1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -307,6 +346,10 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
 
     auto row_out = [&](int q, int row, int advbits, const float* su, const float* sn) {
         const float pde = prolong(wrow[q], (advbits >> q) & 1);
+        if (MODE == MODE_PDEU) {
+            if (active) st_stream(op + (size_t)q * FW, pde);
+            return;
+        }
         const float uu = su[q * FW];
         if (MODE == MODE_UPDATE) {
             const float v = HAS_NN ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
@@ -326,15 +369,17 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         const float* su = su_base + (size_t)s * 2 * lay.ustage;
         const float* sn = sn_base + (size_t)s * 2 * lay.nstage;
         const int advbits = advp[t];
-        mbar_wait(&full[s], (t / kStages) & 1);
+        if (MODE != MODE_PDEU) mbar_wait(&full[s], (t / kStages) & 1);
         if (r0 + kStageRows <= re) {
 #pragma unroll
             for (int q = 0; q < kStageRows; ++q) row_out(q, r0 + q, advbits, su, sn);
         } else {
             for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sn);   // ragged last band
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);                  // this warp is done with slot s
+        if (MODE != MODE_PDEU) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done with slot s
+        }
         wrow += kStageRows;
         if (op) op += (size_t)kStageRows * FW;
         if (MODE == MODE_INPUTS) { unp += (size_t)kStageRows * PW; if (pnp) pnp += (size_t)kStageRows * PW; }

@@ -4,7 +4,9 @@
 // or without the duplicated endpoint.
 //
 // Layout: u, v are [B, H, W] fp32, W contiguous.  One CTA = (32k-column chunk,
-// row band, sample).  A thread owns one column and walks down the band:
+// PAIR of row bands, sample).  A thread owns one column and walks down both bands
+// in lockstep, the two rows packed in float2 so every stencil FMA is one
+// Blackwell FFMA2 (packed fp32x2: the kernel is issue-slot bound, not FMA bound):
 //   * x-direction (rows) taps live in a register window of 2*HALO+ROWS values,
 //     fed by one coalesced global load per new row -> each value is read from
 //     HBM/L2 once per band (+ 2*HALO rows of band overlap);
@@ -31,37 +33,61 @@ struct FineParams {
     float dt, rdx, rdy, rdx2, rdy2;
 };
 
-constexpr int kFineRows = 4;
+#ifndef PPNN_FINE_ROWS
+#define PPNN_FINE_ROWS 4
+#endif
+#ifndef PPNN_FINE_MINCTA
+#define PPNN_FINE_MINCTA 3
+#endif
+constexpr int kFineRows = PPNN_FINE_ROWS;
 
 __device__ __forceinline__ int wrap_pt(int i, int n, int period) {
     if (i < 0) i += period; else if (i >= n) i -= period;
     return clampi(i, 0, n - 1);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot, two rows ----
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float c, float2 x, float2 acc) { return __ffma2_rn(f2(c), x, acc); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+// (c <= 0) * fwd + (c > 0) * bwd for finite operands (a NaN centre poisons both branches anyway)
+__device__ __forceinline__ float sel1(float c, float f, float b) { return c <= 0.f ? f : b; }
+
+// sign-switched one-sided derivative of both rows; the switch is the sign of `c`
+// (the differentiated field itself at the output point, operators.py:255-258)
 template <int HL>
-__device__ __forceinline__ float upwind_sel(const FineParams& p, float c, const float* w /* w[0..2HL], centre at HL */) {
-    float f = 0.f, b = 0.f;
+__device__ __forceinline__ float2 upwind2(const FineParams& p, float2 c, const float2* w /* centre at HL */) {
+    float2 f = f2(0.f), b = f2(0.f);
 #pragma unroll
-    for (int k = 0; k <= HL; ++k) { f += p.af[k] * w[HL + k]; b += p.ab[k] * w[k]; }
-    return c <= 0.f ? f : (c > 0.f ? b : 0.f);
+    for (int k = 0; k <= HL; ++k) { f = fma2(p.af[k], w[HL + k], f); b = fma2(p.ab[k], w[k], b); }
+    return make_float2(sel1(c.x, f.x, b.x), sel1(c.y, f.y, b.y));
 }
 
 template <int HL>
-__device__ __forceinline__ float central_sum(const FineParams& p, const float* w) {
-    float s = 0.f;
+__device__ __forceinline__ float2 central2(const FineParams& p, const float2* w) {
+    float2 s = f2(0.f);
 #pragma unroll
-    for (int k = 0; k <= 2 * HL; ++k) s += p.d[k] * w[k];
+    for (int k = 0; k <= 2 * HL; ++k) s = fma2(p.d[k], w[k], s);
     return s;
 }
 
+__device__ __forceinline__ float2 react2(float2 acc, int react, float2 u1, float2 v1) {
+    return make_float2(add_reaction(acc.x, react, u1.x, v1.x), add_reaction(acc.y, react, u1.y, v1.y));
+}
+
+// One CTA = (column chunk, PAIR of row bands A/B, sample).  A thread owns one
+// column and advances row i of band A and row i of band B in lockstep, the two
+// rows packed in float2 so that every stencil FMA is one FFMA2.
 template <int HL, int MODE>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, PPNN_FINE_MINCTA)
 fine_step_kernel(const FineParams p) {
     constexpr int R = kFineRows;
     constexpr int WIN = 2 * HL + R;
     constexpr bool VWIN = MODE != FINE_AS_WRITTEN;
     constexpr int NF = VWIN ? 2 : 1;                 // fields exchanged through smem
-    extern __shared__ float sm[];                    // [2][NF][R][pitch]
+    extern __shared__ float2 sm2[];                  // [2][NF][R][pitch] of (band A, band B)
     const int TX = blockDim.x, tid = threadIdx.x;
     const int pitch = TX + 2 * HL;
     const int b = blockIdx.z;
@@ -69,47 +95,57 @@ fine_step_kernel(const FineParams p) {
     const int j = j0 + tid;
     const bool active = j < p.W;
     const int jl = wrap_pt(j, p.W, p.PW);            // column this thread loads (wrapped past the edge)
-    const int r0 = blockIdx.y * p.band_rows;
-    const int r1 = min(r0 + p.band_rows, p.H);
+    const int BH = p.band_rows;                      // rows per band; the pair covers 2*BH rows
+    const int rA = blockIdx.y * 2 * BH;              // first row of band A
+    const int rB = rA + BH;                          // first row of band B (may be >= H: empty band)
+    const int endA = min(rA + BH, p.H), endB = min(rB + BH, p.H);
     const size_t plane = (size_t)p.H * p.W;
     const float* ub = p.u + (size_t)b * plane;
     const float* vb = p.v + (size_t)b * plane;
     float* uob = p.uo + (size_t)b * plane;
     float* vob = p.vo + (size_t)b * plane;
     const float mu = __ldg(p.mu + b);
+    // rows never wrap inside a pair that stays clear of both ends of the plane
+    const bool interior = rA - HL >= 0 && rB + BH + HL <= p.H;
 
-    // chunk-edge halo duty: thread t < R*2*HL fetches one (row, side, offset)
+    // chunk-edge halo duty: thread t < R*2*HL fetches one (row, side, offset) of both bands
     const bool halo_duty = tid < R * 2 * HL;
     const int hq = tid / (2 * HL), hs = tid % (2 * HL);
     const int hcol = wrap_pt(hs < HL ? j0 - HL + hs : j0 + TX + (hs - HL), p.W, p.PW);
     const int hslot = hs < HL ? hs : TX + hs;        // position in the smem row
 
-    float wu[WIN], wv[VWIN ? WIN : 1];
+    auto rowptr = [&](const float* base, int r) -> const float* {   // row r of the periodic plane
+        return base + (size_t)(interior ? r : wrap_pt(r, p.H, p.PH)) * p.W;
+    };
+
+    float2 wu[WIN], wv[VWIN ? WIN : 1];
 #pragma unroll
     for (int k = 0; k < 2 * HL; ++k) {
-        int r = wrap_pt(r0 - HL + k, p.H, p.PH);
-        wu[k] = __ldg(ub + (size_t)r * p.W + jl);
-        if (VWIN) wv[k] = __ldg(vb + (size_t)r * p.W + jl);
+        wu[k] = make_float2(__ldg(rowptr(ub, rA - HL + k) + jl), __ldg(rowptr(ub, rB - HL + k) + jl));
+        if (VWIN) wv[k] = make_float2(__ldg(rowptr(vb, rA - HL + k) + jl), __ldg(rowptr(vb, rB - HL + k) + jl));
     }
 
     int buf = 0;
-    for (int i = r0; i < r1; i += R, buf ^= 1) {
-        float vc[R];
-        float hu = 0.f, hv = 0.f;
+    for (int i = 0; i < BH; i += R, buf ^= 1) {
+        float2 vc[R];
+        float2 hu = f2(0.f), hv = f2(0.f);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            int r = wrap_pt(i + q + HL, p.H, p.PH);
-            wu[2 * HL + q] = __ldg(ub + (size_t)r * p.W + jl);
-            if (VWIN) wv[2 * HL + q] = __ldg(vb + (size_t)r * p.W + jl);
-            else vc[q] = (active && i + q < r1) ? __ldg(vb + (size_t)(i + q) * p.W + j) : 0.f;
+            const int ra = rA + i + q + HL, rb = rB + i + q + HL;
+            wu[2 * HL + q] = make_float2(__ldg(rowptr(ub, ra) + jl), __ldg(rowptr(ub, rb) + jl));
+            if (VWIN) wv[2 * HL + q] = make_float2(__ldg(rowptr(vb, ra) + jl), __ldg(rowptr(vb, rb) + jl));
+            else {
+                const int ca = min(rA + i + q, p.H - 1), cb = min(rB + i + q, p.H - 1);
+                vc[q] = make_float2(__ldg(vb + (size_t)ca * p.W + jl), __ldg(vb + (size_t)cb * p.W + jl));
+            }
         }
         if (halo_duty) {
-            int r = min(i + hq, p.H - 1);
-            hu = __ldg(ub + (size_t)r * p.W + hcol);
-            if (VWIN) hv = __ldg(vb + (size_t)r * p.W + hcol);
+            const int ca = min(rA + i + hq, p.H - 1), cb = min(rB + i + hq, p.H - 1);
+            hu = make_float2(__ldg(ub + (size_t)ca * p.W + hcol), __ldg(ub + (size_t)cb * p.W + hcol));
+            if (VWIN) hv = make_float2(__ldg(vb + (size_t)ca * p.W + hcol), __ldg(vb + (size_t)cb * p.W + hcol));
         }
-        float* su = sm + (size_t)buf * NF * R * pitch;
-        float* sv = su + R * pitch;
+        float2* su = sm2 + (size_t)buf * NF * R * pitch;
+        float2* sv = su + R * pitch;
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             su[q * pitch + HL + tid] = wu[HL + q];
@@ -122,56 +158,64 @@ fine_step_kernel(const FineParams p) {
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            int ii = i + q;
-            if (ii >= r1) break;
-            float yu[2 * HL + 1];
+            const int ia = rA + i + q, ib = rB + i + q;
+            if (ia >= endA) break;                   // band A is never shorter than band B
+            float2 yu[2 * HL + 1];
 #pragma unroll
             for (int k = 0; k <= 2 * HL; ++k) yu[k] = su[q * pitch + tid + k];
-            const float c = wu[HL + q];
-            float unew, vnew;
+            const float2 c = wu[HL + q];
+            float2 unew, vnew;
             if (MODE == FINE_GENERIC) {
-                float yv[2 * HL + 1];
+                float2 yv[2 * HL + 1];
 #pragma unroll
                 for (int k = 0; k <= 2 * HL; ++k) yv[k] = sv[q * pitch + tid + k];
-                const float cv = wv[HL + q];
-                float ru = 0.f, rv = 0.f;
+                const float2 cv = wv[HL + q];
+                float2 ru = f2(0.f), rv = f2(0.f);
                 if (p.rhs_u & PPNN_RHS_ADV)
-                    ru = (-c * upwind_sel<HL>(p, c, wu + q)) * p.rdx - (cv * upwind_sel<HL>(p, c, yu)) * p.rdy;
+                    ru = add2(mul2(mul2(neg2(c), upwind2<HL>(p, c, wu + q)), f2(p.rdx)),
+                              neg2(mul2(mul2(cv, upwind2<HL>(p, c, yu)), f2(p.rdy))));
                 if (p.rhs_u & PPNN_RHS_DIFF) {
-                    float lap = mu * (central_sum<HL>(p, wu + q) * p.rdx2 + central_sum<HL>(p, yu) * p.rdy2);
-                    ru = (p.rhs_u & PPNN_RHS_ADV) ? ru + lap : lap;
+                    float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, wu + q), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
+                    ru = (p.rhs_u & PPNN_RHS_ADV) ? add2(ru, lap) : lap;
                 }
-                ru = add_reaction(ru, p.rhs_u & ~3, c, cv);
+                ru = react2(ru, p.rhs_u & ~3, c, cv);
                 if (p.rhs_v & PPNN_RHS_ADV)
-                    rv = (-c * upwind_sel<HL>(p, cv, wv + q)) * p.rdx - (cv * upwind_sel<HL>(p, cv, yv)) * p.rdy;
+                    rv = add2(mul2(mul2(neg2(c), upwind2<HL>(p, cv, wv + q)), f2(p.rdx)),
+                              neg2(mul2(mul2(cv, upwind2<HL>(p, cv, yv)), f2(p.rdy))));
                 if (p.rhs_v & PPNN_RHS_DIFF) {
-                    float lap = mu * (central_sum<HL>(p, wv + q) * p.rdx2 + central_sum<HL>(p, yv) * p.rdy2);
-                    rv = (p.rhs_v & PPNN_RHS_ADV) ? rv + lap : lap;
+                    float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, wv + q), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
+                    rv = (p.rhs_v & PPNN_RHS_ADV) ? add2(rv, lap) : lap;
                 }
-                rv = add_reaction(rv, p.rhs_v & ~3, c, cv);
-                unew = c + p.dt * ru;
-                vnew = cv + p.dt * rv;
+                rv = react2(rv, p.rhs_v & ~3, c, cv);
+                unew = fma2(p.dt, ru, c);
+                vnew = fma2(p.dt, rv, cv);
             } else {
                 // burgers2Dpu then burgers2Dpv with the updated u (operators.py:474-475)
-                const float dxu = upwind_sel<HL>(p, c, wu + q), dyu = upwind_sel<HL>(p, c, yu);
-                const float lapu = mu * (central_sum<HL>(p, wu + q) * p.rdx2 + central_sum<HL>(p, yu) * p.rdy2);
-                const float vcen = VWIN ? wv[HL + q] : vc[q];
-                unew = c + p.dt * ((-c * dxu) * p.rdx - (vcen * dyu) * p.rdy + lapu);
+                const float2 dxu = upwind2<HL>(p, c, wu + q), dyu = upwind2<HL>(p, c, yu);
+                const float2 lapu = mul2(f2(mu), add2(mul2(central2<HL>(p, wu + q), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
+                const float2 vcen = VWIN ? wv[HL + q] : vc[q];
+                const float2 advy = neg2(mul2(mul2(vcen, dyu), f2(p.rdy)));
+                unew = fma2(p.dt, add2(add2(mul2(mul2(neg2(c), dxu), f2(p.rdx)), advy), lapu), c);
                 if (MODE == FINE_AS_WRITTEN) {
                     // quirk Q3: v is advected and diffused with u's derivative fields
-                    vnew = vcen + p.dt * ((-unew * dxu) * p.rdx - (vcen * dyu) * p.rdy + lapu);
+                    vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxu), f2(p.rdx)), advy), lapu), vcen);
                 } else {
-                    float yv[2 * HL + 1];
+                    float2 yv[2 * HL + 1];
 #pragma unroll
                     for (int k = 0; k <= 2 * HL; ++k) yv[k] = sv[q * pitch + tid + k];
-                    const float dxv = upwind_sel<HL>(p, vcen, wv + q), dyv = upwind_sel<HL>(p, vcen, yv);
-                    const float lapv = mu * (central_sum<HL>(p, wv + q) * p.rdx2 + central_sum<HL>(p, yv) * p.rdy2);
-                    vnew = vcen + p.dt * ((-unew * dxv) * p.rdx - (vcen * dyv) * p.rdy + lapv);
+                    const float2 dxv = upwind2<HL>(p, vcen, wv + q), dyv = upwind2<HL>(p, vcen, yv);
+                    const float2 lapv = mul2(f2(mu), add2(mul2(central2<HL>(p, wv + q), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
+                    vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxv), f2(p.rdx)),
+                                                neg2(mul2(mul2(vcen, dyv), f2(p.rdy)))), lapv), vcen);
                 }
             }
             if (active) {
-                uob[(size_t)ii * p.W + j] = unew;
-                vob[(size_t)ii * p.W + j] = vnew;
+                uob[(size_t)ia * p.W + j] = unew.x;
+                vob[(size_t)ia * p.W + j] = vnew.x;
+                if (ib < endB) {
+                    uob[(size_t)ib * p.W + j] = unew.y;
+                    vob[(size_t)ib * p.W + j] = vnew.y;
+                }
             }
         }
 #pragma unroll
@@ -192,23 +236,28 @@ static int launch_fine(const FineParams& p, int B, void* stream) {
     int TX = wpc * 32;
     if (TX < kFineRows * 2 * HL) TX = ((kFineRows * 2 * HL + 31) / 32) * 32;
     nchunk = (p.W + TX - 1) / TX;
-    // row bands: enough CTAs for ~4 waves of 148 SMs x 3 resident CTAs, bands >= 32 rows
+    // band pairs: enough CTAs for ~4 waves of 148 SMs x 3 resident CTAs, bands >= 16 rows
     long want = 148L * 3 * 4;
-    long per_band_ctas = (long)nchunk * B;
-    int nband = (int)((want + per_band_ctas - 1) / per_band_ctas);
-    int max_band = (p.H + 31) / 32;
-    if (nband > max_band) nband = max_band;
-    if (nband < 1) nband = 1;
-    int band_rows = (p.H + nband - 1) / nband;
+    long per_pair_ctas = (long)nchunk * B;
+    int npair = (int)((want + per_pair_ctas - 1) / per_pair_ctas);
+    int max_pair = (p.H + 31) / 32;
+    if (npair > max_pair) npair = max_pair;
+    if (npair < 1) npair = 1;
+    int band_rows = (p.H + 2 * npair - 1) / (2 * npair);
     band_rows = (band_rows + kFineRows - 1) / kFineRows * kFineRows;
-    nband = (p.H + band_rows - 1) / band_rows;
+    npair = (p.H + 2 * band_rows - 1) / (2 * band_rows);
     FineParams q = p;
     q.band_rows = band_rows;
     constexpr int NF = MODE == FINE_AS_WRITTEN ? 1 : 2;
-    size_t smem = (size_t)2 * NF * kFineRows * (TX + 2 * HL) * sizeof(float);
-    dim3 grid(nchunk, nband, B);
-    if (nband > 65535 || B > 65535) return PPNN_E_SHAPE;
-    fine_step_kernel<HL, MODE><<<grid, TX, smem, (cudaStream_t)stream>>>(q);
+    size_t smem = (size_t)2 * NF * kFineRows * (TX + 2 * HL) * sizeof(float2);
+    dim3 grid(nchunk, npair, B);
+    if (npair > 65535 || B > 65535) return PPNN_E_SHAPE;
+    auto kern = fine_step_kernel<HL, MODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, TX, smem, (cudaStream_t)stream>>>(q);
     return launch_status();
 }
 

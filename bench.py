@@ -154,7 +154,7 @@ def cpu_oracle_step_fn(B):
     return run, B * 2 * F * F
 
 
-def time_cpu(B, min_seconds=10.0, max_reps=20):
+def time_cpu(B, min_seconds=12.0, max_reps=400):
     run, pts = cpu_oracle_step_fn(B)
     run()                                                   # warm-up
     t0 = time.perf_counter()
@@ -336,6 +336,34 @@ def run_ours(args):
         t = timed(lambda: fbi.step_(a, b_, mf, a2, b2), reps * 2, 3)
         extras["fine_burgers_step_intended_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
                                                         "hbm_gbs": 8 * fpts / t / 1e6}
+
+        # rollout (train2D.py:230-245): K1 -> network -> K2 per step, CUDA-graph replayed,
+        # around a random-weight network with the layer shapes of cnn2dRich (ppnn_b200/nets.py)
+        try:
+            from ppnn_b200.nets import ConvResNet
+            torch.manual_seed(1)
+            net = ConvResNet(True).to(dev).eval()
+            rstats = dict(inmean=torch.zeros(1, 2, 1, 1), instd=torch.full((1, 2, 1, 1), 0.3),
+                          pdemean=torch.zeros(1, 2, 1, 1), pdestd=torch.full((1, 2, 1, 1), 1e-3),
+                          outmean=torch.tensor(STATS["outmean"]).reshape(1, 2, 1, 1),
+                          outstd=torch.tensor(STATS["outstd"]).reshape(1, 2, 1, 1),
+                          mumean=torch.tensor(0.75, device=dev), mustd=torch.tensor(0.35, device=dev))
+            T = 100
+            for nb, tag in ((CASE["num_para"], "rollout_100steps_B12"), (96, "rollout_100steps_B96")):
+                u0 = u[:nb].clone()
+                m0 = mu[:nb].clone()
+                step.rollout(net, u0, m0, rstats, 3, uses_pde=True, graph=True)      # warm-up (cudnn, capture)
+                barrier()
+                t0 = time.perf_counter()
+                res = step.rollout(net, u0, m0, rstats, T, uses_pde=True, graph=True)
+                torch.cuda.synchronize()
+                dt_roll = time.perf_counter() - t0
+                extras[tag] = {"seconds": dt_roll, "traj_per_s": world * nb / dt_roll, "steps": T,
+                               "finite": bool(torch.isfinite(res).all()),
+                               "note": "includes graph capture; K1 + ConvResNet(1.55M params, fp32/cudnn) + K2 per step"}
+                del res
+        except Exception as exc:   # the rollout extra must never take the headline down
+            extras["rollout_error"] = repr(exc)[:300]
 
     clocks = sampler.stop() if sampler else None
 

@@ -82,11 +82,16 @@ def gather_shards(local: torch.Tensor, n_total: int, group=None) -> Optional[tor
     rank, ws = world()
     if ws == 1 or not (dist.is_available() and dist.is_initialized()):
         return local
-    sizes = [shard_bounds(n_total, r, ws) for r in range(ws)]
-    pieces = [torch.empty((hi - lo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-              for lo, hi in sizes] if rank == 0 else None
-    dist.gather(local.contiguous(), pieces, dst=0, group=group)
-    return torch.cat(pieces, dim=0) if rank == 0 else None
+    sizes = [hi - lo for lo, hi in (shard_bounds(n_total, r, ws) for r in range(ws))]
+    nmax = max(sizes)
+    # collectives need equal shapes: pad the ragged shards to the largest one, trim after
+    padded = local.contiguous()
+    if padded.shape[0] < nmax:
+        pad = torch.zeros((nmax - padded.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded = torch.cat((padded, pad), dim=0)
+    pieces = [torch.empty_like(padded) for _ in range(ws)] if rank == 0 else None
+    dist.gather(padded, pieces, dst=0, group=group)
+    return torch.cat([p[:n] for p, n in zip(pieces, sizes)], dim=0) if rank == 0 else None
 
 
 def shard_file(path: str, rank: int, world_size: int) -> str:

@@ -385,6 +385,40 @@ def test_rollout_drift_100_steps(pk):
     assert d_ours[-1] < 1e-4
 
 
+def test_network_rollout_eager_graph_and_oracle(pk):
+    """train2D.py:230-245 around a random-weight network: eager vs CUDA-graph replay
+    vs the CPU oracle driving the same network."""
+    from ppnn_b200.nets import ConvResNet
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(5)
+        c = CASES["rd_p"]
+        g = load_golden("pde_du_257.npz")
+        u0 = torch.cat((g["u257"], g["u257"].flip(1) * 0.8), 0)
+        mu = torch.tensor([0.3, 1.1]).reshape(-1, 1, 1, 1)
+        st = dict(inmean=torch.tensor([0.05, -0.1]).reshape(1, 2, 1, 1), instd=torch.tensor([0.4, 0.5]).reshape(1, 2, 1, 1),
+                  pdemean=torch.tensor([1e-4, -1e-4]).reshape(1, 2, 1, 1), pdestd=torch.tensor([2e-3, 3e-3]).reshape(1, 2, 1, 1),
+                  outmean=torch.tensor([1e-4, -2e-4]).reshape(1, 2, 1, 1), outstd=torch.tensor([3e-3, 2e-3]).reshape(1, 2, 1, 1),
+                  mumean=torch.tensor(0.75), mustd=torch.tensor(0.35))
+        for uses_pde in (True, False):
+            net = ConvResNet(uses_pde).eval()
+            ostep = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+            with torch.no_grad():
+                ref = torch.stack(O.ppnn_rollout(ostep, net, u0, mu, st, 3, uses_pde=uses_pde), dim=1)
+            step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+            netc = net.cuda()
+            eager = step.rollout(netc, u0.cuda(), mu.cuda(), st, 3, uses_pde=uses_pde, graph=False)
+            graph = step.rollout(netc, u0.cuda(), mu.cuda(), st, 3, uses_pde=uses_pde, graph=True)
+            assert eager.shape == ref.shape == (2, 3, 2, 257, 257)
+            # the random-weight network (cuDNN on the GPU, native conv on the CPU) is the noisy
+            # part here, not the PDE path: its fp32 differences feed back through 3 steps
+            assert_parity(eager.cpu(), ref, 3e-4, f"rollout eager uses_pde={uses_pde}")
+            assert_parity(graph.cpu(), eager.cpu(), 2e-6, f"rollout graph uses_pde={uses_pde}")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 def test_batch_independence_and_linearity_at_scale(pk):
     """Size-independent properties at a batch the oracle cannot afford:
     (i) every sample of a large batch equals the same sample run alone;
@@ -414,3 +448,25 @@ def test_no_cpu_fallback(pk):
         pk["mesh"](65, 9, dim=2).down(torch.zeros(1, 1, 65, 65))
     with pytest.raises(RuntimeError):
         pk["FineBurgers"]().step(torch.zeros(1, 1, 33, 33), torch.zeros(1, 1, 33, 33), torch.zeros(1))
+
+
+def test_datagen_sharding_snapshots_and_oracle(pk):
+    """python -m ppnn_b200.datagen (operators.py:403-492): the union of two shards equals
+    the one-process run bit for bit, snapshots follow the reference loop (i % every == 0),
+    and the trajectories match the oracle run from the same initial conditions."""
+    from ppnn_b200 import datagen, dist as D
+    kw = dict(mesh=65, para=3, repeat=2, steps=13, every=4, seed=10)
+    one = datagen.generate(rank=0, world_size=1, **kw)
+    assert one.shape == (6, 4, 2, 65, 65)
+    two = torch.cat([datagen.generate(rank=r, world_size=2, **kw) for r in range(2)], dim=0)
+    assert torch.equal(one, two)
+    nog = datagen.generate(rank=0, world_size=1, graph=False, **kw)
+    assert torch.equal(one, nog)
+    coef = D.fourier_coefficients(10, 0, 6)
+    u0 = datagen.fourier_initial_condition(coef[:, 0], 65, "cuda").cpu()
+    v0 = datagen.fourier_initial_condition(coef[:, 1], 65, "cuda").cpu()
+    assert abs(u0.min().item() - 0.1) < 1e-6 and abs(u0.max().item() - 1.1) < 1e-6
+    mu = torch.linspace(0.025, 0.065, 3).repeat(2).reshape(-1, 1, 1, 1)
+    _, _, su, sv = O.fine_burgers_run(u0, v0, mu, 13, every=4)
+    ref = torch.stack((torch.cat(su, dim=1), torch.cat(sv, dim=1)), dim=2)
+    assert_parity(one, ref, TOL, "datagen vs oracle")

@@ -80,9 +80,13 @@ __device__ __forceinline__ float2 react2(float2 acc, int react, float2 u1, float
 // One CTA = (column chunk, PAIR of row bands A/B, sample).  A thread owns one
 // column and advances row i of band A and row i of band B in lockstep, the two
 // rows packed in float2 so that every stencil FMA is one FFMA2.
-template <int HL, int MODE>
+// WC: compile-time row pitch (0 = runtime) so that the streamed accesses of a batch are
+// one pointer + immediates; pairs that stay clear of the plane ends never wrap rows and
+// take a branch-free addressing path.
+template <int HL, int MODE, int WC>
 __global__ void __launch_bounds__(384, PPNN_FINE_MINCTA)
 fine_step_kernel(const FineParams p) {
+    const int W = WC ? WC : p.W;
     constexpr int R = kFineRows;
     constexpr int WIN = 2 * HL + R;
     constexpr bool VWIN = MODE != FINE_AS_WRITTEN;
@@ -93,13 +97,13 @@ fine_step_kernel(const FineParams p) {
     const int b = blockIdx.z;
     const int j0 = blockIdx.x * TX;
     const int j = j0 + tid;
-    const bool active = j < p.W;
-    const int jl = wrap_pt(j, p.W, p.PW);            // column this thread loads (wrapped past the edge)
+    const bool active = j < W;
+    const int jl = wrap_pt(j, W, p.PW);            // column this thread loads (wrapped past the edge)
     const int BH = p.band_rows;                      // rows per band; the pair covers 2*BH rows
     const int rA = blockIdx.y * 2 * BH;              // first row of band A
     const int rB = rA + BH;                          // first row of band B (may be >= H: empty band)
     const int endA = min(rA + BH, p.H), endB = min(rB + BH, p.H);
-    const size_t plane = (size_t)p.H * p.W;
+    const size_t plane = (size_t)p.H * W;
     const float* ub = p.u + (size_t)b * plane;
     const float* vb = p.v + (size_t)b * plane;
     float* uob = p.uo + (size_t)b * plane;
@@ -111,11 +115,11 @@ fine_step_kernel(const FineParams p) {
     // chunk-edge halo duty: thread t < R*2*HL fetches one (row, side, offset) of both bands
     const bool halo_duty = tid < R * 2 * HL;
     const int hq = tid / (2 * HL), hs = tid % (2 * HL);
-    const int hcol = wrap_pt(hs < HL ? j0 - HL + hs : j0 + TX + (hs - HL), p.W, p.PW);
+    const int hcol = wrap_pt(hs < HL ? j0 - HL + hs : j0 + TX + (hs - HL), W, p.PW);
     const int hslot = hs < HL ? hs : TX + hs;        // position in the smem row
 
     auto rowptr = [&](const float* base, int r) -> const float* {   // row r of the periodic plane
-        return base + (size_t)(interior ? r : wrap_pt(r, p.H, p.PH)) * p.W;
+        return base + (size_t)wrap_pt(r, p.H, p.PH) * W;
     };
 
     float2 wu[WIN], wv[VWIN ? WIN : 1];
@@ -125,24 +129,56 @@ fine_step_kernel(const FineParams p) {
         if (VWIN) wv[k] = make_float2(__ldg(rowptr(vb, rA - HL + k) + jl), __ldg(rowptr(vb, rB - HL + k) + jl));
     }
 
+    // fast-path pointers: window-feed rows (r + HL) and centre rows r of both bands, this thread's column
+    const float* fuA = ub + (size_t)(rA + HL) * W + jl;
+    const float* fuB = ub + (size_t)(rB + HL) * W + jl;
+    const float* fvA = vb + (size_t)(rA + (VWIN ? HL : 0)) * W + jl;
+    const float* fvB = vb + (size_t)(rB + (VWIN ? HL : 0)) * W + jl;
+    const float* huA = ub + (size_t)(rA + hq) * W + hcol;      // halo duty: centre row rA + i + hq
+    const float* huB = ub + (size_t)(rB + hq) * W + hcol;
+    const float* hvA = vb + (size_t)(rA + hq) * W + hcol;
+    const float* hvB = vb + (size_t)(rB + hq) * W + hcol;
+
+    // output pointers (rows rA + i, rB + i of this thread's column; only dereferenced when in range)
+    float* ouA = uob + (size_t)rA * W + j;
+    float* ouB = uob + (size_t)rB * W + j;
+    float* ovA = vob + (size_t)rA * W + j;
+    float* ovB = vob + (size_t)rB * W + j;
+
     int buf = 0;
     for (int i = 0; i < BH; i += R, buf ^= 1) {
         float2 vc[R];
         float2 hu = f2(0.f), hv = f2(0.f);
+        if (interior) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int ra = rA + i + q + HL, rb = rB + i + q + HL;
-            wu[2 * HL + q] = make_float2(__ldg(rowptr(ub, ra) + jl), __ldg(rowptr(ub, rb) + jl));
-            if (VWIN) wv[2 * HL + q] = make_float2(__ldg(rowptr(vb, ra) + jl), __ldg(rowptr(vb, rb) + jl));
-            else {
-                const int ca = min(rA + i + q, p.H - 1), cb = min(rB + i + q, p.H - 1);
-                vc[q] = make_float2(__ldg(vb + (size_t)ca * p.W + jl), __ldg(vb + (size_t)cb * p.W + jl));
+            for (int q = 0; q < R; ++q) {
+                wu[2 * HL + q] = make_float2(__ldg(fuA + (size_t)q * W), __ldg(fuB + (size_t)q * W));
+                if (VWIN) wv[2 * HL + q] = make_float2(__ldg(fvA + (size_t)q * W), __ldg(fvB + (size_t)q * W));
+                else vc[q] = make_float2(__ldg(fvA + (size_t)q * W), __ldg(fvB + (size_t)q * W));
             }
-        }
-        if (halo_duty) {
-            const int ca = min(rA + i + hq, p.H - 1), cb = min(rB + i + hq, p.H - 1);
-            hu = make_float2(__ldg(ub + (size_t)ca * p.W + hcol), __ldg(ub + (size_t)cb * p.W + hcol));
-            if (VWIN) hv = make_float2(__ldg(vb + (size_t)ca * p.W + hcol), __ldg(vb + (size_t)cb * p.W + hcol));
+            if (halo_duty) {
+                hu = make_float2(__ldg(huA), __ldg(huB));
+                if (VWIN) hv = make_float2(__ldg(hvA), __ldg(hvB));
+            }
+            fuA += (size_t)R * W; fuB += (size_t)R * W; fvA += (size_t)R * W; fvB += (size_t)R * W;
+            huA += (size_t)R * W; huB += (size_t)R * W;
+            if (VWIN) { hvA += (size_t)R * W; hvB += (size_t)R * W; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int ra = rA + i + q + HL, rb = rB + i + q + HL;
+                wu[2 * HL + q] = make_float2(__ldg(rowptr(ub, ra) + jl), __ldg(rowptr(ub, rb) + jl));
+                if (VWIN) wv[2 * HL + q] = make_float2(__ldg(rowptr(vb, ra) + jl), __ldg(rowptr(vb, rb) + jl));
+                else {
+                    const int ca = min(rA + i + q, p.H - 1), cb = min(rB + i + q, p.H - 1);
+                    vc[q] = make_float2(__ldg(vb + (size_t)ca * W + jl), __ldg(vb + (size_t)cb * W + jl));
+                }
+            }
+            if (halo_duty) {
+                const int ca = min(rA + i + hq, p.H - 1), cb = min(rB + i + hq, p.H - 1);
+                hu = make_float2(__ldg(ub + (size_t)ca * W + hcol), __ldg(ub + (size_t)cb * W + hcol));
+                if (VWIN) hv = make_float2(__ldg(vb + (size_t)ca * W + hcol), __ldg(vb + (size_t)cb * W + hcol));
+            }
         }
         float2* su = sm2 + (size_t)buf * NF * R * pitch;
         float2* sv = su + R * pitch;
@@ -210,11 +246,11 @@ fine_step_kernel(const FineParams p) {
                 }
             }
             if (active) {
-                uob[(size_t)ia * p.W + j] = unew.x;
-                vob[(size_t)ia * p.W + j] = vnew.x;
+                ouA[(size_t)q * W] = unew.x;
+                ovA[(size_t)q * W] = vnew.x;
                 if (ib < endB) {
-                    uob[(size_t)ib * p.W + j] = unew.y;
-                    vob[(size_t)ib * p.W + j] = vnew.y;
+                    ouB[(size_t)q * W] = unew.y;
+                    ovB[(size_t)q * W] = vnew.y;
                 }
             }
         }
@@ -223,6 +259,7 @@ fine_step_kernel(const FineParams p) {
             wu[k] = wu[k + R];
             if (VWIN) wv[k] = wv[k + R];
         }
+        ouA += (size_t)R * W; ouB += (size_t)R * W; ovA += (size_t)R * W; ovB += (size_t)R * W;
     }
 }
 
@@ -252,7 +289,13 @@ static int launch_fine(const FineParams& p, int B, void* stream) {
     size_t smem = (size_t)2 * NF * kFineRows * (TX + 2 * HL) * sizeof(float2);
     dim3 grid(nchunk, npair, B);
     if (npair > 65535 || B > 65535) return PPNN_E_SHAPE;
-    auto kern = fine_step_kernel<HL, MODE>;
+    void (*kern)(FineParams) = fine_step_kernel<HL, MODE, 0>;
+    if (HL == 3) {                       // the generator's stencil: specialise the usual mesh widths
+        if (p.W == 257) kern = fine_step_kernel<HL == 3 ? 3 : HL, MODE, 257>;
+        else if (p.W == 1025) kern = fine_step_kernel<HL == 3 ? 3 : HL, MODE, 1025>;
+        else if (p.W == 1024) kern = fine_step_kernel<HL == 3 ? 3 : HL, MODE, 1024>;
+        else if (p.W == 256) kern = fine_step_kernel<HL == 3 ? 3 : HL, MODE, 256>;
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

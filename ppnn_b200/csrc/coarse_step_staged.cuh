@@ -18,6 +18,7 @@
 // fetched with ordinary loads, so nothing outside the tensor is ever read.
 #pragma once
 #include "coarse_common.cuh"
+#include "tma.cuh"
 
 namespace ppnn {
 
@@ -30,28 +31,6 @@ namespace ppnn {
 constexpr int kStageRows = PPNN_STAGE_ROWS;   // kStageRows * FW must be a multiple of 4 (constant lead)
 constexpr int kStages = PPNN_STAGES;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    const uint32_t a = smem_u32(bar);
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 // L2 eviction-priority policies: the restriction gather touches sectors that the
 // TMA stream re-reads tens of microseconds later -> keep them (evict_last); the
 // streamed bands themselves are dead after one use (evict_first).
@@ -89,10 +68,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 
 struct StagedLayout {
     int ustage;      // floats per (stage, group) u buffer: kStageRows*FW + 8 (lead / tail slack), 16 B multiple
@@ -101,9 +76,6 @@ struct StagedLayout {
     int nsteps;      // ring steps = max over groups of ceil(rows / kStageRows)
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 producer warp
 constexpr int kGatherBatch = 5;                     // coarse points per thread whose loads are issued together

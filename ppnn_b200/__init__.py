@@ -9,12 +9,14 @@ on PYTHONPATH, or import from here):
     ppnn_b200.rhs            burgers2D{F,p,diffuse,W}{u,v}, rd{F,p}{u,v}, diff*, convec*, ks1d
     ppnn_b200.utility.utils  mesh_convertor, model_count
 Tier B (fully fused):
-    ppnn_b200.fused          CoarseStep (pde_du, step_inputs, step_update, rollouts), FineBurgers
+    ppnn_b200.fused          CoarseStep (pde_du, step_inputs, step_update, rollouts), FineBurgers, FineRhsSolver
+    ppnn_b200.datagen        sharded dataset generation (python -m ppnn_b200.datagen)
+    ppnn_b200.dist           sample sharding / global statistics helpers
 
 All device work goes through the C ABI of ``libppnn_b200.so`` (include/ppnn_b200.h).
 There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .fused import CoarseStep, FineBurgers  # noqa: F401
+from .fused import CoarseStep, FineBurgers, FineRhsSolver  # noqa: F401
 
-__all__ = ["CoarseStep", "FineBurgers", "operators", "rhs", "utility"]
+__all__ = ["CoarseStep", "FineBurgers", "FineRhsSolver", "operators", "rhs", "utility"]

@@ -381,3 +381,37 @@ class FineBurgers:
                     one(i)
                     i += 1
         return u, v, su, sv
+
+
+class FineRhsSolver:
+    """Generic fused explicit Euler step on the fine grid: ``u, v <- u + dt*rhsu(u, v), v + dt*rhsv(u, v)``
+    for any pair of ``rhs.py`` names (both right-hand sides see the OLD state, like ``pde_du``),
+    with Upwind1(``adv_accuracy``) / Central2(``diff_accuracy``) stencils sharing one halo -- the kernel
+    family of the commented reaction-diffusion / diffusion / convection generators of
+    operators.py:494-748 (``ppnn_fine_rhs_step``)."""
+
+    def __init__(self, rhsu: str, rhsv: str, dt: float, dx: float, dy: Optional[float] = None,
+                 adv_accuracy: int = 3, diff_accuracy: int = 6, endpoint: bool = True):
+        self.rhs_u, self.rhs_v = RHS_IDS[rhsu], RHS_IDS[rhsv]
+        self.dt, self.dx, self.dy = float(dt), float(dx), float(dx if dy is None else dy)
+        self.adv_accuracy, self.diff_accuracy = int(adv_accuracy), int(diff_accuracy)
+        self.endpoint = bool(endpoint)
+
+    def step_(self, u, v, muv, uo, vo) -> None:
+        lib = L.load()
+        B, H, W = u.shape[0], u.shape[-2], u.shape[-1]
+        L.check(lib.ppnn_fine_rhs_step(u.data_ptr(), v.data_ptr(), muv.data_ptr(), uo.data_ptr(), vo.data_ptr(),
+                                       B, H, W, int(self.endpoint), self.rhs_u, self.rhs_v,
+                                       self.adv_accuracy, self.diff_accuracy,
+                                       self.dt, self.dx, self.dy, L.stream()), "ppnn_fine_rhs_step")
+
+    @torch.no_grad()
+    def step(self, u, v, mu) -> Tuple[torch.Tensor, torch.Tensor]:
+        u, v = L.dev(u, "u"), L.dev(v, "v")
+        if u.shape != v.shape:
+            raise RuntimeError("u and v must have the same shape")
+        muv = _mu_vec(mu, u.shape[0], u.device)
+        uo, vo = torch.empty_like(u), torch.empty_like(v)
+        with torch.cuda.device(u.device):
+            self.step_(u, v, muv, uo, vo)
+        return uo, vo

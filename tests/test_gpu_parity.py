@@ -324,7 +324,8 @@ def test_fine_solver_against_reference_golden(pk, mode):
 
 
 @pytest.mark.parametrize("n,endpoint,aa,da", [(257, True, 3, 6), (256, False, 3, 6), (100, True, 1, 2),
-                                               (131, False, 2, 4), (1025, True, 3, 6)])
+                                               (131, False, 2, 4), (1025, True, 3, 6), (1024, False, 3, 6),
+                                               (513, True, 2, 4), (640, False, 1, 2)])
 def test_fine_solver_sizes_and_accuracies(pk, n, endpoint, aa, da):
     gen = torch.Generator().manual_seed(31)
     b = 2
@@ -470,3 +471,28 @@ def test_datagen_sharding_snapshots_and_oracle(pk):
     _, _, su, sv = O.fine_burgers_run(u0, v0, mu, 13, every=4)
     ref = torch.stack((torch.cat(su, dim=1), torch.cat(sv, dim=1)), dim=2)
     assert_parity(one, ref, TOL, "datagen vs oracle")
+
+
+@pytest.mark.parametrize("n,endpoint", [(129, True), (1025, True), (512, False)])
+def test_fine_generic_rhs_step(pk, n, endpoint):
+    """ppnn_fine_rhs_step: Jacobi Euler step for rhs.py name pairs (both kernels: register-window
+    for narrow meshes, TMA-fed for wide ones) against the oracle's rhs on fine-grid halos."""
+    import ppnn_b200
+    gen = torch.Generator().manual_seed(61)
+    b = 2
+    u = O.fourier_initial_condition(torch.randn(b, 81, 2, generator=gen), n) - 0.55
+    v = O.fourier_initial_condition(torch.randn(b, 81, 2, generator=gen), n) - 0.6
+    mu = torch.tensor([0.3, 1.1]).reshape(-1, 1, 1, 1)
+    dt, dx = 1e-5, 0.025
+    o = O.Ops(adv_accuracy=3, diff_accuracy=6)
+    px, py = (O.fine_wrap_x, O.fine_wrap_y) if endpoint else (O.wrap_x, O.wrap_y)
+    for ru, rv in (("rdFu", "rdFv"), ("burgers2DFu", "burgers2DFv"), ("diffu", "convecv")):
+        ur = u + dt * O.rhs(ru, u, v, mu, o, px(u, 3), py(u, 3), dx, dx, dx ** 2, dx ** 2)
+        vr = v + dt * O.rhs(rv, u, v, mu, o, px(v, 3), py(v, 3), dx, dx, dx ** 2, dx ** 2)
+        solver = ppnn_b200.FineRhsSolver(ru, rv, dt, dx, endpoint=endpoint)
+        uo, vo = solver.step(u.cuda(), v.cuda(), mu.cuda())
+        ulp = torch.finfo(torch.float32).eps
+        assert_parity(uo.cpu(), ur, TOL, f"{ru} {n}")
+        assert_parity(vo.cpu(), vr, TOL, f"{rv} {n}")
+        assert (uo.cpu() - ur).abs().max() <= 4 * ulp * ur.abs().max()
+        assert (vo.cpu() - vr).abs().max() <= 4 * ulp * vr.abs().max()

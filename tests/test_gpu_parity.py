@@ -496,3 +496,44 @@ def test_fine_generic_rhs_step(pk, n, endpoint):
         assert_parity(vo.cpu(), vr, TOL, f"{rv} {n}")
         assert (uo.cpu() - ur).abs().max() <= 4 * ulp * ur.abs().max()
         assert (vo.cpu() - vr).abs().max() <= 4 * ulp * vr.abs().max()
+
+
+def test_unrolled_training_gradients_reach_the_network(pk):
+    """BASELINE config 3: backward through a 2-step unrolled rollout (fused step + adjoint kernel)
+    gives the same network-parameter gradients as autograd through the CPU oracle."""
+    from ppnn_b200.nets import ConvResNet
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(9)
+        c = CASES["burgers_f"]
+        g = load_golden("pde_du_257.npz")
+        u0 = g["u257"]
+        mu = torch.tensor([0.05]).reshape(1, 1, 1, 1)
+        target = u0.flip(1) * 0.5
+        om, os_ = torch.tensor([0.0, 0.0]).reshape(1, 2, 1, 1), torch.tensor([1e-2, 2e-2]).reshape(1, 2, 1, 1)
+        net = ConvResNet(uses_pde=False)
+        ostep = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+
+        def rollout(stepfn, net_, u, mu_, om_, os__):
+            for _ in range(2):
+                nn_out = net_((u[:, :, :-1, :-1]) / 0.3, (mu_ - 0.045) / 0.017)
+                u = stepfn(u, mu_, nn_out, om_, os__)
+            return u
+
+        ref_out = rollout(lambda u, m, n, a, b: O.ppnn_update(u, ostep.pde_du(u, m), n, a, b), net, u0, mu, om, os_)
+        loss_ref = torch.nn.functional.mse_loss(ref_out, target)
+        gref = torch.autograd.grad(loss_ref, list(net.parameters()))
+        step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+        netc = ConvResNet(uses_pde=False)
+        netc.load_state_dict(net.state_dict())
+        netc = netc.cuda()
+        out = rollout(step.step_update, netc, u0.cuda(), mu.cuda(), om, os_)
+        loss = torch.nn.functional.mse_loss(out, target.cuda())
+        gours = torch.autograd.grad(loss, list(netc.parameters()))
+        assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+        num = sum(((a.cpu().double() - b.double()) ** 2).sum() for a, b in zip(gours, gref)) ** 0.5
+        den = sum((b.double() ** 2).sum() for b in gref) ** 0.5
+        assert den > 0 and (num / den).item() < 2e-3, f"parameter-gradient mismatch {num / den:.3e}"
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -16,28 +16,43 @@ struct RhsParams {
     long total;
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int kRhsRows = 4;     // output rows per thread: the x-direction window is loaded once for all of them
+
+// thread = column j, kRhsRows consecutive output rows; grid (column chunks, row groups, samples)
+template <int K>
+__global__ void __launch_bounds__(128)
 rhs2d_kernel(const RhsParams p) {
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-         idx += (long)gridDim.x * blockDim.x) {
-        int j = (int)(idx % p.W);
-        long t = idx / p.W;
-        int i = (int)(t % p.H);
-        long b = t / p.H;
-        const float mu = __ldg(p.mu + b);
-        const float u1 = ld_stream(p.u1 + idx), v1 = ld_stream(p.v1 + idx);
-        const float* cx = p.ax + ((size_t)b * (p.H + 2 * p.halo) + i) * p.W + j;        // rows i .. i+K-1
-        const float* cy = p.ay + ((size_t)b * p.H + i) * (p.W + 2 * p.halo) + j;        // cols j .. j+K-1
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.W) return;
+    const int i0 = blockIdx.y * kRhsRows;
+    const long b = blockIdx.z;
+    const int Wy = p.W + 2 * p.halo;
+    const float mu = __ldg(p.mu + b);
+    const float* cx = p.ax + ((size_t)b * (p.H + 2 * p.halo) + i0) * p.W + j;     // padded rows i0 .. i0+K+kRhsRows-2
+    float xw[K + kRhsRows - 1];
+#pragma unroll
+    for (int k = 0; k < K + kRhsRows - 1; ++k)
+        xw[k] = (i0 + k < p.H + 2 * p.halo) ? ld_stream(cx + (size_t)k * p.W) : 0.f;
+#pragma unroll
+    for (int q = 0; q < kRhsRows; ++q) {
+        const int i = i0 + q;
+        if (i >= p.H) break;
+        const size_t o = ((size_t)b * p.H + i) * p.W + j;
+        const float u1 = ld_stream(p.u1 + o), v1 = ld_stream(p.v1 + o);
+        const float* cy = p.ay + ((size_t)b * p.H + i) * Wy + j;                   // padded cols j .. j+K-1
+        float yw[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) yw[k] = __ldg(cy + k);
         float acc = 0.f;
         if (p.rhs_id & PPNN_RHS_ADV) {
             float fx = 0.f, bx = 0.f, fy = 0.f, by = 0.f;
-            for (int k = 0; k < p.K; ++k) {
-                float xv = __ldg(cx + (size_t)k * p.W), yv = __ldg(cy + k);
-                fx += p.aa[k] * xv; fy += p.aa[k] * yv;
-                bx += p.ab[k] * xv; by += p.ab[k] * yv;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fx += p.aa[k] * xw[q + k]; fy += p.aa[k] * yw[k];
+                bx += p.ab[k] * xw[q + k]; by += p.ab[k] * yw[k];
             }
             if (p.adv_upwind) {
-                float c1 = __ldg(cx + (size_t)p.halo * p.W), c2 = __ldg(cy + p.halo);
+                const float c1 = xw[q + (K - 1) / 2], c2 = yw[(K - 1) / 2];
                 fx = c1 <= 0.f ? fx : (c1 > 0.f ? bx : 0.f);
                 fy = c2 <= 0.f ? fy : (c2 > 0.f ? by : 0.f);
             }
@@ -45,15 +60,20 @@ rhs2d_kernel(const RhsParams p) {
         }
         if (p.rhs_id & PPNN_RHS_DIFF) {
             float lx = 0.f, ly = 0.f;
-            for (int k = 0; k < p.K; ++k) {
-                lx += p.d[k] * __ldg(cx + (size_t)k * p.W);
-                ly += p.d[k] * __ldg(cy + k);
-            }
-            float lap = mu * (lx / p.dx2 + ly / p.dy2);
+#pragma unroll
+            for (int k = 0; k < K; ++k) { lx += p.d[k] * xw[q + k]; ly += p.d[k] * yw[k]; }
+            const float lap = mu * (lx / p.dx2 + ly / p.dy2);
             acc = (p.rhs_id & PPNN_RHS_ADV) ? acc + lap : lap;
         }
-        st_stream(p.out + idx, add_reaction(acc, p.rhs_id & ~3, u1, v1));
+        st_stream(p.out + o, add_reaction(acc, p.rhs_id & ~3, u1, v1));
     }
+}
+
+template <int K>
+static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
+    dim3 grid((p.W + 127) / 128, (p.H + kRhsRows - 1) / kRhsRows, (unsigned)B);
+    rhs2d_kernel<K><<<grid, 128, 0, s>>>(p);
+    return launch_status();
 }
 
 }  // namespace ppnn
@@ -88,8 +108,14 @@ extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
     p.H = H; p.W = W; p.halo = halo; p.rhs_id = rhs_id; p.adv_upwind = adv_scheme == PPNN_UPWIND1;
     p.dx = dx; p.dy = dy; p.dx2 = dx2; p.dy2 = dy2;
     p.total = (long)B * H * W;
-    long blocks = (p.total + 255) / 256;
-    if (blocks > 148L * 16) blocks = 148L * 16;
-    rhs2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    return launch_status();
+    if (B > 65535 || (H + kRhsRows - 1) / kRhsRows > 65535) return PPNN_E_SHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.K) {
+    case 1: return launch_rhs2d<1>(p, B, s);
+    case 3: return launch_rhs2d<3>(p, B, s);
+    case 5: return launch_rhs2d<5>(p, B, s);
+    case 7: return launch_rhs2d<7>(p, B, s);
+    case 9: return launch_rhs2d<9>(p, B, s);
+    }
+    return PPNN_E_HALO;
 }

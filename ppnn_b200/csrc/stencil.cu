@@ -54,21 +54,24 @@ stencil_x_kernel(const StencilParams p) {
         if (i0 + q < p.Hout) st_stream(out + (size_t)(i0 + q) * p.Wout, apply_taps<K, UPWIND>(p, w + q));
 }
 
-// ---- along W (axis 3): grid (col groups, rows, planes) -----------------------
+// ---- along W (axis 3): grid (col groups, row runs, planes) ---------------------
 template <int K, bool UPWIND>
 __global__ void __launch_bounds__(128)
 stencil_y_kernel(const StencilParams p) {
     int jg = (blockIdx.x * blockDim.x + threadIdx.x) * kVec;
     if (jg >= p.Wout) return;
-    int i = blockIdx.y;
-    const float* in = p.in + ((size_t)blockIdx.z * p.Hin + i) * p.Win + jg;
-    float* out = p.out + ((size_t)blockIdx.z * p.Hout + i) * p.Wout + jg;
-    float w[K + kVec - 1];
+    const int i0 = blockIdx.y * kRows;
+    const float* in = p.in + ((size_t)blockIdx.z * p.Hin + i0) * p.Win + jg;
+    float* out = p.out + ((size_t)blockIdx.z * p.Hout + i0) * p.Wout + jg;
+    const int rows = min(kRows, p.Hout - i0);
+    for (int r = 0; r < rows; ++r, in += p.Win, out += p.Wout) {
+        float w[K + kVec - 1];
 #pragma unroll
-    for (int k = 0; k < K + kVec - 1; ++k) w[k] = (jg + k < p.Win) ? __ldg(in + k) : 0.f;
+        for (int k = 0; k < K + kVec - 1; ++k) w[k] = (jg + k < p.Win) ? __ldg(in + k) : 0.f;
 #pragma unroll
-    for (int q = 0; q < kVec; ++q)
-        if (jg + q < p.Wout) st_stream(out + q, apply_taps<K, UPWIND>(p, w + q));
+        for (int q = 0; q < kVec; ++q)
+            if (jg + q < p.Wout) st_stream(out + q, apply_taps<K, UPWIND>(p, w + q));
+    }
 }
 
 // ---- adjoint: grad_in[m] = sum_k coef(o = m-k)[k] * g[o], thread per element --
@@ -114,7 +117,7 @@ static int launch_fwd(const StencilParams& p, long planes, int axis, cudaStream_
         stencil_x_kernel<K, UPWIND><<<grid, 128, 0, s>>>(p);
     } else {
         int groups = (p.Wout + kVec - 1) / kVec;
-        dim3 grid((groups + 127) / 128, p.Hout, (unsigned)planes);
+        dim3 grid((groups + 127) / 128, (p.Hout + kRows - 1) / kRows, (unsigned)planes);
         stencil_y_kernel<K, UPWIND><<<grid, 128, 0, s>>>(p);
     }
     return launch_status();
@@ -162,7 +165,6 @@ extern "C" int ppnn_stencil_fwd(const float* in, float* out, long planes, int Hi
     int st = check_geometry(planes, Hin, Win, axis, ta.n, &p.Hout, &p.Wout);
     if (st != PPNN_OK) return st;
     if (planes == 0) return PPNN_OK;
-    if (axis == 3 && p.Hout > 65535) return PPNN_E_SHAPE;
     p.in = in; p.out = out; p.Hin = Hin; p.Win = Win; p.centre = accuracy;
     for (int k = 0; k < kMaxTaps; ++k) { p.a[k] = ta.c[k]; p.b[k] = scheme == PPNN_UPWIND1 ? tb.c[k] : 0.f; }
     const bool up = scheme == PPNN_UPWIND1;

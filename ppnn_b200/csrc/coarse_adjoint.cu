@@ -264,6 +264,8 @@ coarse_adjoint_kernel(const CoarseParams p, const AdjParams a) {
 }
 
 }  // namespace ppnn
+#include <cstdlib>
+#include "coarse_adjoint_staged.cuh"
 
 using namespace ppnn;
 
@@ -284,6 +286,36 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
     if (support > kMaxSupport) return PPNN_E_TOOBIG;
     if (support > p.FW) support = p.FW;
     a.support = support;
+    // staged path: (sample, field) CTAs in 2-CTA clusters, TMA ring (coarse_adjoint_staged.cuh)
+    {
+        AdjStagedLayout lay;
+        lay.wmain = ((p.FW - 1) % 32 == 0) ? p.FW - 1 : p.FW;
+        lay.nchunk = (lay.wmain + 31) / 32;
+        lay.apitch = a.apitch; lay.support = support;
+        lay.gstage = (kAdjStageRows * p.FW + 8 + 3) & ~3;
+        lay.split = p.FH;
+        if (2 * lay.nchunk <= kAdjWarps && p.FH >= 4 * kAdjStageRows)
+            lay.split = ((p.FH / 2 + kAdjStageRows - 1) / kAdjStageRows) * kAdjStageRows;
+        int n0 = (lay.split + kAdjStageRows - 1) / kAdjStageRows;
+        int n1 = (p.FH - lay.split + kAdjStageRows - 1) / kAdjStageRows;
+        lay.nsteps = n0 > n1 ? n0 : n1;
+        const int nn2 = p.NH * p.NW;
+        size_t un = (size_t)kAdjStages * 2 * lay.gstage;
+        if (un < (size_t)2 * nn2) un = (size_t)2 * nn2;
+        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3) * sizeof(int) +
+                       ((size_t)((p.CW * support + 3) & ~3) + ((nn2 + 3) & ~3) + (((size_t)p.CH * lay.apitch + 3) & ~(size_t)3) + un) * sizeof(float);
+        if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 110 * 1024 &&
+            grad_u != grad_out && !getenv("PPNN_NO_TMA")) {
+            void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
+            if (p.FW == 257) kern = add_identity ? coarse_adjoint_staged_kernel<257, true> : coarse_adjoint_staged_kernel<257, false>;
+            else             kern = add_identity ? coarse_adjoint_staged_kernel<0, true> : coarse_adjoint_staged_kernel<0, false>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+            const float* g_end = grad_out + (size_t)B * 2 * p.FH * p.FW;
+            kern<<<2 * B, kAdjThreads, smem2, (cudaStream_t)stream>>>(p, a, lay, g_end);
+            return launch_status();
+        }
+    }
     size_t smem = (size_t)4 * p.NH * p.NW * sizeof(float) + (size_t)p.FH * (sizeof(float4) + sizeof(int)) +
                   (size_t)p.CW * sizeof(int) + (size_t)p.CW * support * sizeof(float) +
                   (size_t)2 * p.CH * a.apitch * sizeof(float);

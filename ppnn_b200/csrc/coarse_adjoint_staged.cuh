@@ -1,0 +1,330 @@
+// Staged adjoint of pde_du for meshes the staged forward kernel takes (the reference
+// mesh, 257): the mirror image of coarse_step_staged.cuh.
+//
+// One CTA = one (sample, field) plane of grad_out; the two CTAs of a sample form a
+// 2-CTA thread-block CLUSTER and exchange their coarse cotangents through
+// distributed shared memory, so each CTA writes only its own plane of grad_u:
+//
+//   phase 1  a producer warp streams 4-row bands of grad_out (two row groups)
+//            through a shared-memory ring with cp.async.bulk + mbarriers; consumer
+//            warps (row group, 32-column chunk) write grad_u = grad_out (the identity
+//            of u + pde_du(u)) or 0 and accumulate the H-pass of the bicubic
+//            transpose in a 4-slot register window, flushed into A[I][j] (shared,
+//            atomics only where the two row groups meet)
+//   phase 2  W-pass of the bicubic transpose through an inverse weight table, fold of
+//            the duplicated endpoint (transpose of padBC_rd), times dt  -> q_f
+//   phase 0' restriction gather of the coarse state (recomputed, nothing was saved);
+//            it reuses the ring's memory, which is dead by now
+//   -------- cluster.sync: q_u and q_v are visible to both CTAs --------
+//   phase 3  for the CTA's own field: transposed stencils of its right-hand side,
+//            point-wise Jacobians of BOTH right-hand sides (the other one's q read
+//            from the peer CTA's shared memory), grad_mu partial sums
+//   phase 4  transpose of the bilinear restriction: <= 4 atomic adds per coarse point
+//            into the CTA's own plane (after its own base values, same CTA => ordered)
+#pragma once
+#include <cooperative_groups.h>
+#include "coarse_common.cuh"
+#include "tma.cuh"
+
+namespace ppnn {
+
+namespace cg = cooperative_groups;
+
+constexpr int kAdjStageRows = 4;
+constexpr int kAdjStages = 4;
+constexpr int kAdjWarps = 16;                       // consumer warps
+constexpr int kAdjThreads = (kAdjWarps + 1) * 32;   // + producer warp
+
+struct AdjStagedLayout {
+    int gstage;     // floats per (slot, group) band buffer: rows*FW + 8, multiple of 4
+    int split;      // first row of the second row group (multiple of kAdjStageRows); FH = single group
+    int nsteps;
+    int apitch;     // odd pitch of A rows
+    int support;    // inverse W-pass table width
+    int nchunk, wmain;
+};
+
+template <int FWC, bool IDENT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAdjThreads, 2)
+coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjStagedLayout lay,
+                             const float* g_end) {
+    constexpr int R = kAdjStageRows;
+    extern __shared__ float4 smem4[];
+    float4* roww = smem4;                                        // [FH]
+    int* rowi = reinterpret_cast<int*>(roww + p.FH);             // [FH]
+    int* rowadv = rowi + p.FH;                                   // [2][nsteps]
+    int* jstart = rowadv + 2 * lay.nsteps;                       // [CW]
+    const int nn2 = p.NH * p.NW;
+    float* wt = reinterpret_cast<float*>(rowi + ((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3));   // [CW][support]
+    float* q = wt + ((p.CW * lay.support + 3) & ~3);             // [nn2]   same offset in both CTAs of the cluster
+    float* A = q + ((nn2 + 3) & ~3);                             // [CH][apitch]
+    float* un = A + (((size_t)p.CH * lay.apitch + 3) & ~(size_t)3);   // union: ring [stages][2][gstage] | cu, cv
+    float* ring = un;
+    float* cu = un;
+    float* cv = cu + nn2;
+    __shared__ __align__(8) uint64_t full[kAdjStages];
+    __shared__ __align__(8) uint64_t empty[kAdjStages];
+    __shared__ float red[32];
+    __shared__ float mu_partial;
+
+    const int FW = FWC ? FWC : p.FW;
+    const int b = blockIdx.x >> 1, f = blockIdx.x & 1;           // f == rank in the cluster
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t plane = (size_t)p.FH * FW;
+    const float* ub = a.u + (size_t)b * 2 * plane;
+    const float* gf = a.g + ((size_t)b * 2 + f) * plane;         // this CTA's plane of grad_out
+    float* of = a.gu + ((size_t)b * 2 + f) * plane;              // ... and of grad_u
+    const float mu = __ldg(a.mu + b);
+    const int ngroups = lay.split < p.FH ? 2 : 1;
+    const int nconsumers = min(ngroups * lay.nchunk, kAdjWarps);
+    const bool producer = warp == kAdjWarps;
+
+    auto issue = [&](int t) {
+        const int s = t % kAdjStages;
+        uintptr_t a0[2]; uint32_t nb[2] = {0, 0}; uint32_t total = 0;
+        const uintptr_t end_al = reinterpret_cast<uintptr_t>(g_end) & ~(uintptr_t)15;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
+            const int r0 = rs + t * R;
+            if (g >= ngroups || r0 >= re) continue;
+            const int nrows = min(R, re - r0);
+            const uintptr_t ad = reinterpret_cast<uintptr_t>(gf + (size_t)r0 * FW);
+            a0[g] = ad & ~(uintptr_t)15;
+            nb[g] = (uint32_t)((ad - a0[g]) + (size_t)nrows * FW * 4 + 15) & ~15u;
+            if (a0[g] + nb[g] > end_al) {                        // last copy of the tensor: stay inside it
+                float* dst = ring + ((size_t)s * 2 + g) * lay.gstage;
+                for (const float* qq = reinterpret_cast<const float*>(end_al); qq < g_end; ++qq)
+                    dst[(reinterpret_cast<uintptr_t>(qq) - a0[g]) >> 2] = *qq;
+                nb[g] = (uint32_t)(end_al - a0[g]);
+            }
+            total += nb[g];
+        }
+        mbar_expect_tx(&full[s], total);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            if (nb[g]) bulk_g2s(ring + ((size_t)s * 2 + g) * lay.gstage, reinterpret_cast<const void*>(a0[g]), nb[g], &full[s]);
+    };
+
+    if (producer) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kAdjStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
+            fence_barrier_init();
+            for (int t = 0; t < kAdjStages && t < lay.nsteps; ++t) issue(t);
+        }
+    } else {
+        // tables and a cleared accumulator while the first bands fly
+        for (int i = tid; i < p.FH; i += kAdjWarps * 32) {
+            float w[4]; int i0;
+            cubic_entry(p.suh, i, &i0, w);
+            rowi[i] = i0;
+            roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+        }
+        for (int e = tid; e < 2 * lay.nsteps; e += kAdjWarps * 32) {
+            const int g = e >= lay.nsteps, t = e - g * lay.nsteps;
+            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
+            int bits = 0;
+            for (int qq = 0; qq < R; ++qq) {
+                const int i = rs + t * R + qq;
+                if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << qq;
+            }
+            rowadv[e] = bits;
+        }
+        for (int J = tid; J < p.CW; J += kAdjWarps * 32) {
+            int js = (int)ceilf((float)(J - 2) / p.suw) - 1;
+            jstart[J] = js < 0 ? 0 : js;
+        }
+        for (int idx = tid; idx < p.CH * lay.apitch; idx += kAdjWarps * 32) A[idx] = 0.f;
+    }
+    __syncthreads();
+    if (!producer) {
+        for (int idx = tid; idx < p.CW * lay.support; idx += kAdjWarps * 32) {
+            int J = idx / lay.support, k = idx - J * lay.support;
+            int j = jstart[J] + k;
+            float wsum = 0.f;
+            if (j < FW) {
+                float w[4]; int j0;
+                cubic_entry(p.suw, j, &j0, w);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (clampi(j0 - 1 + t, 0, p.CW - 1) == J) wsum += w[t];
+            }
+            wt[idx] = wsum;
+        }
+    }
+
+    // ---- phase 1a: the duplicated-endpoint column (one element per row), point-wise ----
+    if (!producer && lay.wmain < FW) {
+        const int jc = FW - 1;
+        for (int i = tid; i < p.FH; i += kAdjWarps * 32) {
+            const float gv = ld_stream(gf + (size_t)i * FW + jc);
+            st_stream(of + (size_t)i * FW + jc, IDENT ? gv : 0.f);
+            const int i0 = rowi[i];
+            const float4 wx = roww[i];
+            atomicAdd(A + clampi(i0 - 1, 0, p.CH - 1) * lay.apitch + jc, wx.x * gv);
+            atomicAdd(A + clampi(i0,     0, p.CH - 1) * lay.apitch + jc, wx.y * gv);
+            atomicAdd(A + clampi(i0 + 1, 0, p.CH - 1) * lay.apitch + jc, wx.z * gv);
+            atomicAdd(A + clampi(i0 + 2, 0, p.CH - 1) * lay.apitch + jc, wx.w * gv);
+        }
+    }
+
+    // ---- phase 1b: the other columns, streamed through the ring ---------------------
+    if (producer) {
+        if (lane == 0) {
+            for (int t = kAdjStages; t < lay.nsteps; ++t) {
+                mbar_wait(&empty[t % kAdjStages], ((t / kAdjStages) - 1) & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t);
+            }
+        }
+    } else if (warp < nconsumers) {
+        const int g = warp / lay.nchunk;
+        const int chunk = warp - g * lay.nchunk;
+        const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
+        const int j = chunk * 32 + lane;
+        const bool active = j < lay.wmain;
+        const int jc = active ? j : lay.wmain - 1;
+        const int lead = (int)(reinterpret_cast<uintptr_t>(gf) & 15) >> 2;
+        const float* sg_base = ring + (size_t)g * lay.gstage + lead + jc;
+        float* op = of + (size_t)rs * FW + jc;
+        float* Af = A + jc;
+        const float4* wrow = roww + rs;
+        const int* advp = rowadv + g * lay.nsteps;
+        int base = rowi[rs];
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;            // accumulators of coarse rows base-1 .. base+2
+        auto row_in = [&](int qq, int advbits, const float* sg) {
+            if ((advbits >> qq) & 1) {                           // retire the oldest slot (warp-uniform)
+                if (active) atomicAdd(Af + clampi(base - 1, 0, p.CH - 1) * lay.apitch, c0);
+                c0 = c1; c1 = c2; c2 = c3; c3 = 0.f;
+                ++base;
+            }
+            const float gv = sg[qq * FW];
+            const float4 wx = wrow[qq];
+            c0 += wx.x * gv; c1 += wx.y * gv; c2 += wx.z * gv; c3 += wx.w * gv;
+            if (active) st_stream(op + (size_t)qq * FW, IDENT ? gv : 0.f);
+        };
+        for (int t = 0; t < lay.nsteps; ++t) {
+            const int s = t % kAdjStages;
+            const int r0 = rs + t * R;
+            const float* sg = sg_base + (size_t)s * 2 * lay.gstage;
+            const int advbits = advp[t];
+            mbar_wait(&full[s], (t / kAdjStages) & 1);
+            if (r0 + R <= re) {
+#pragma unroll
+                for (int qq = 0; qq < R; ++qq) row_in(qq, advbits, sg);
+            } else {
+                for (int qq = 0; r0 + qq < re; ++qq) row_in(qq, advbits, sg);     // ragged last band
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            wrow += R;
+            op += (size_t)R * FW;
+        }
+        if (active) {
+            atomicAdd(Af + clampi(base - 1, 0, p.CH - 1) * lay.apitch, c0);
+            atomicAdd(Af + clampi(base,     0, p.CH - 1) * lay.apitch, c1);
+            atomicAdd(Af + clampi(base + 1, 0, p.CH - 1) * lay.apitch, c2);
+            atomicAdd(Af + clampi(base + 2, 0, p.CH - 1) * lay.apitch, c3);
+        }
+    }
+    __syncthreads();              // A complete, ring dead, this CTA's base values of grad_u written
+
+    // ---- phase 2 (W-pass, fold, dt) and phase 0' (gather into the dead ring) ----
+    const int rid_own = f ? p.rhs_v : p.rhs_u, rid_oth = f ? p.rhs_u : p.rhs_v;
+    const bool both = ((rid_own | rid_oth) & PPNN_RHS_ADV) || ((rid_own | rid_oth) & ~3);
+    const int nthr = kAdjThreads;
+    for (int idx = tid; idx < nn2; idx += nthr) {
+        int Jp = idx / p.NH, Ip = idx - Jp * p.NH;                // lanes vary in I: A pitch is odd
+        float sum = 0.f;
+        for (int ej = 0; ej < 2; ++ej) {
+            if (ej && Jp != 0) break;
+            int J = ej ? p.NW : Jp;
+            const float* w = wt + J * lay.support;
+            int js = jstart[J];
+            int cnt = min(lay.support, FW - js);
+            for (int ei = 0; ei < 2; ++ei) {
+                if (ei && Ip != 0) break;
+                int I = ei ? p.NH : Ip;
+                const float* row = A + I * lay.apitch + js;
+                float t = 0.f;
+                for (int k = 0; k < cnt; ++k) t += w[k] * row[k];
+                sum += t;
+            }
+        }
+        q[Ip * p.NW + Jp] = p.dt * sum;
+    }
+    {
+        const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
+#pragma unroll 4
+        for (int idx = lo + tid; idx < hi; idx += nthr) {
+            int g = idx >= nn2;
+            int r = idx - g * nn2;
+            int I = r / p.NW, J = r - I * p.NW;
+            cu[idx] = restrict_point(p, ub + g * plane, I, J);
+        }
+    }
+    // grad_mu partial of this field (needs only local data)
+    __syncthreads();
+    const float* own = f ? cv : cu;
+    float part = 0.f;
+    if (a.gmu && (rid_own & PPNN_RHS_DIFF))
+        for (int idx = tid; idx < nn2; idx += nthr) {
+            int I = idx / p.NW, J = idx - I * p.NW;
+            part += (central_x(p, own, I, J) / p.dx2 + central_y(p, own, I, J) / p.dy2) * q[idx];
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        float v = lane < (kAdjThreads >> 5) ? red[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) mu_partial = v;
+    }
+
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();               // q and mu_partial of both CTAs are complete
+
+    // ---- phase 3 + 4: own field's coarse cotangent, scatter through D_down^T ------
+    const float* q_oth = cluster.map_shared_rank(q, f ^ 1);
+    if (f == 0 && tid == 0 && a.gmu) a.gmu[b] = mu_partial + *cluster.map_shared_rank(&mu_partial, 1);
+    for (int idx = tid; idx < nn2; idx += nthr) {
+        int I = idx / p.NW, J = idx - I * p.NW;
+        const float q_own = q[idx];
+        float cot = stencil_adjoint(p, rid_own, own, cu, cv, q, I, J, mu);
+        float q_o = 0.f;
+        if (both) {
+            q_o = q_oth[idx];
+            const float u1 = cu[idx], v1 = cv[idx];
+            const float* oth = f ? cu : cv;
+            // point-wise factors: rhs_g contains (-u1*Dx(g))/dx - (v1*Dy(g))/dy
+            if (f == 0) {        // d/du1
+                if (rid_own & PPNN_RHS_ADV) cot += -upwind_x(p, own, I, J) / p.dx * q_own;
+                if (rid_oth & PPNN_RHS_ADV) cot += -upwind_x(p, oth, I, J) / p.dx * q_o;
+            } else {             // d/dv1
+                if (rid_own & PPNN_RHS_ADV) cot += -upwind_y(p, own, I, J) / p.dy * q_own;
+                if (rid_oth & PPNN_RHS_ADV) cot += -upwind_y(p, oth, I, J) / p.dy * q_o;
+            }
+            float du, dv;
+            reaction_jac(rid_own & ~3, u1, v1, &du, &dv);
+            cot += (f ? dv : du) * q_own;
+            reaction_jac(rid_oth & ~3, u1, v1, &du, &dv);
+            cot += (f ? dv : du) * q_o;
+        }
+        BilinearTap t = bilinear_tap(p, I, J);
+        const float h0 = 1.f - t.li, w0 = 1.f - t.lj;
+        float* o = of + (size_t)t.i0 * FW + t.j0;
+        atomicAdd(o, h0 * w0 * cot);
+        if (t.lj != 0.f) atomicAdd(o + t.dj, h0 * t.lj * cot);
+        if (t.li != 0.f) {
+            float* o2 = o + (size_t)t.di * FW;
+            atomicAdd(o2, t.li * w0 * cot);
+            if (t.lj != 0.f) atomicAdd(o2 + t.dj, t.li * t.lj * cot);
+        }
+    }
+    cluster.sync();               // the peer may still be reading this CTA's shared memory
+}
+
+}  // namespace ppnn

@@ -303,8 +303,8 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
         size_t un = (size_t)kAdjStages * 2 * lay.gstage;
         if (un < (size_t)2 * nn2) un = (size_t)2 * nn2;
         size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3) * sizeof(int) +
-                       ((size_t)((p.CW * support + 3) & ~3) + ((nn2 + 3) & ~3) + (((size_t)p.CH * lay.apitch + 3) & ~(size_t)3) + un) * sizeof(float);
-        if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 110 * 1024 &&
+                       ((size_t)((p.CW * support + 3) & ~3) + ((nn2 + 3) & ~3) + (((size_t)(p.CH + 4) * lay.apitch + 3) & ~(size_t)3) + un) * sizeof(float);
+        if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 112 * 1024 &&
             grad_u != grad_out && !getenv("PPNN_NO_TMA")) {
             void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
             if (p.FW == 257) kern = add_identity ? coarse_adjoint_staged_kernel<257, true> : coarse_adjoint_staged_kernel<257, false>;

@@ -57,8 +57,8 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     const int nn2 = p.NH * p.NW;
     float* wt = reinterpret_cast<float*>(rowi + ((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3));   // [CW][support]
     float* q = wt + ((p.CW * lay.support + 3) & ~3);             // [nn2]   same offset in both CTAs of the cluster
-    float* A = q + ((nn2 + 3) & ~3);                             // [CH][apitch]
-    float* un = A + (((size_t)p.CH * lay.apitch + 3) & ~(size_t)3);   // union: ring [stages][2][gstage] | cu, cv
+    float* A = q + ((nn2 + 3) & ~3);                             // [CH + 4][apitch]: 4 extra rows = overlap buffer of row group 1
+    float* un = A + (((size_t)(p.CH + 4) * lay.apitch + 3) & ~(size_t)3);   // union: ring [stages][2][gstage] | cu, cv
     float* ring = un;
     float* cu = un;
     float* cv = cu + nn2;
@@ -135,7 +135,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             int js = (int)ceilf((float)(J - 2) / p.suw) - 1;
             jstart[J] = js < 0 ? 0 : js;
         }
-        for (int idx = tid; idx < p.CH * lay.apitch; idx += kAdjWarps * 32) A[idx] = 0.f;
+        for (int idx = tid; idx < (p.CH + 4) * lay.apitch; idx += kAdjWarps * 32) A[idx] = 0.f;
     }
     __syncthreads();
     if (!producer) {
@@ -193,9 +193,19 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         const int* advp = rowadv + g * lay.nsteps;
         int base = rowi[rs];
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;            // accumulators of coarse rows base-1 .. base+2
+        // Every (coarse row, column) entry of A has ONE writer per row group, so flushes are plain
+        // read-modify-writes (shared-memory float atomics are CAS loops).  The two groups only meet
+        // on the 4 coarse rows around the split: group 1 sends those to the overlap rows A[CH..CH+3],
+        // which phase 2 folds back.
+        const int ovl_lo = max(rowi[lay.split < p.FH ? lay.split : 0] - 1, 0);
+        auto flush = [&](int I, float v) {
+            const int r = clampi(I, 0, p.CH - 1);
+            const int rr = (g == 1 && r - ovl_lo < 4) ? p.CH + (r - ovl_lo) : r;
+            if (active) Af[rr * lay.apitch] += v;
+        };
         auto row_in = [&](int qq, int advbits, const float* sg) {
             if ((advbits >> qq) & 1) {                           // retire the oldest slot (warp-uniform)
-                if (active) atomicAdd(Af + clampi(base - 1, 0, p.CH - 1) * lay.apitch, c0);
+                flush(base - 1, c0);
                 c0 = c1; c1 = c2; c2 = c3; c3 = 0.f;
                 ++base;
             }
@@ -221,14 +231,17 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             wrow += R;
             op += (size_t)R * FW;
         }
-        if (active) {
-            atomicAdd(Af + clampi(base - 1, 0, p.CH - 1) * lay.apitch, c0);
-            atomicAdd(Af + clampi(base,     0, p.CH - 1) * lay.apitch, c1);
-            atomicAdd(Af + clampi(base + 1, 0, p.CH - 1) * lay.apitch, c2);
-            atomicAdd(Af + clampi(base + 2, 0, p.CH - 1) * lay.apitch, c3);
-        }
+        flush(base - 1, c0); flush(base, c1); flush(base + 1, c2); flush(base + 2, c3);
     }
     __syncthreads();              // A complete, ring dead, this CTA's base values of grad_u written
+    if (ngroups == 2) {           // fold row group 1's overlap rows back
+        const int ovl_lo = max(rowi[lay.split] - 1, 0);
+        for (int idx = tid; idx < 4 * lay.apitch; idx += kAdjThreads) {
+            const int k = idx / lay.apitch, j = idx - k * lay.apitch;
+            if (ovl_lo + k < p.CH) A[(ovl_lo + k) * lay.apitch + j] += A[(p.CH + k) * lay.apitch + j];
+        }
+        __syncthreads();
+    }
 
     // ---- phase 2 (W-pass, fold, dt) and phase 0' (gather into the dead ring) ----
     const int rid_own = f ? p.rhs_v : p.rhs_u, rid_oth = f ? p.rhs_u : p.rhs_v;

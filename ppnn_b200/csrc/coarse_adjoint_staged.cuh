@@ -154,18 +154,29 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         }
     }
 
-    // ---- phase 1a: the duplicated-endpoint column (one element per row), point-wise ----
+    // ---- phase 1a: the duplicated-endpoint column (one element per row) ------------------
+    // base values point-wise; its H-pass as a gather per coarse row (fixed summation order,
+    // so the result does not depend on thread scheduling)
     if (!producer && lay.wmain < FW) {
         const int jc = FW - 1;
-        for (int i = tid; i < p.FH; i += kAdjWarps * 32) {
-            const float gv = ld_stream(gf + (size_t)i * FW + jc);
-            st_stream(of + (size_t)i * FW + jc, IDENT ? gv : 0.f);
-            const int i0 = rowi[i];
-            const float4 wx = roww[i];
-            atomicAdd(A + clampi(i0 - 1, 0, p.CH - 1) * lay.apitch + jc, wx.x * gv);
-            atomicAdd(A + clampi(i0,     0, p.CH - 1) * lay.apitch + jc, wx.y * gv);
-            atomicAdd(A + clampi(i0 + 1, 0, p.CH - 1) * lay.apitch + jc, wx.z * gv);
-            atomicAdd(A + clampi(i0 + 2, 0, p.CH - 1) * lay.apitch + jc, wx.w * gv);
+        for (int i = tid; i < p.FH; i += kAdjWarps * 32)
+            st_stream(of + (size_t)i * FW + jc, IDENT ? ld_stream(gf + (size_t)i * FW + jc) : 0.f);
+        for (int I = tid; I < p.CH; I += kAdjWarps * 32) {
+            // fine rows whose 4-tap window can reach coarse row I: floor(i*suh) in [I-2, I+1]
+            int ilo = (int)ceilf((float)(I - 2) / p.suh) - 1, ihi = (int)floorf((float)(I + 2) / p.suh) + 1;
+            ilo = max(ilo, 0); ihi = min(ihi, p.FH - 1);
+            float sum = 0.f;
+            for (int i = ilo; i <= ihi; ++i) {
+                const int i0 = rowi[i];
+                const float4 wx = roww[i];
+                float w = 0.f;
+                if (clampi(i0 - 1, 0, p.CH - 1) == I) w += wx.x;
+                if (clampi(i0,     0, p.CH - 1) == I) w += wx.y;
+                if (clampi(i0 + 1, 0, p.CH - 1) == I) w += wx.z;
+                if (clampi(i0 + 2, 0, p.CH - 1) == I) w += wx.w;
+                if (w != 0.f) sum += w * __ldg(gf + (size_t)i * FW + jc);
+            }
+            A[I * lay.apitch + jc] = sum;
         }
     }
 

@@ -537,3 +537,72 @@ def test_unrolled_training_gradients_reach_the_network(pk):
         assert den > 0 and (num / den).item() < 2e-3, f"parameter-gradient mismatch {num / den:.3e}"
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def _embedded(t, offset, guard=64):
+    """Copy of `t` living at element `offset` + guard inside a NaN-filled buffer: (view, buffer)."""
+    buf = torch.full((t.numel() + 2 * guard + 8,), float("nan"), device=t.device)
+    view = buf[guard + offset: guard + offset + t.numel()].view(t.shape)
+    view.copy_(t)
+    return view, buf
+
+
+def _guards_intact(view, buf, guard=64):
+    start = (view.data_ptr() - buf.data_ptr()) // 4
+    return bool(torch.isnan(buf[:start]).all()) and bool(torch.isnan(buf[start + view.numel():]).all())
+
+
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+def test_misaligned_and_end_of_allocation_buffers(pk, offset):
+    """The TMA paths round copies to 16-byte boundaries: tensors that start at any 4-byte phase and
+    that end flush with NaN guard words must give the same results (a guard value leaking into the
+    arithmetic would turn outputs into NaN; a misaligned network output selects the register-path
+    kernel, whose FMA contraction differs by an ulp) and leave the guards untouched."""
+    def same(x, y, what):
+        assert bool(torch.isfinite(x).all()), what + ": non-finite output"
+        assert_parity(x.cpu(), y.cpu(), 2e-6, what)
+
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    c = CASES["burgers_f"]
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    B = 3
+    u = torch.randn(B, 2, 257, 257, device="cuda", generator=gen) * 0.4
+    nn = torch.randn(B, 2, 256, 256, device="cuda", generator=gen)
+    g = torch.randn(B, 2, 257, 257, device="cuda", generator=gen)
+    mu = torch.tensor([0.02, 0.05, 0.07], device="cuda")
+    om, os_ = [0.01, -0.02], [0.3, 0.2]
+    ref_upd = step.step_update(u, mu, nn, om, os_)
+    ref_pde = step.pde_du(u, mu)
+    ur = u.clone().requires_grad_(True)
+    (ref_g,) = torch.autograd.grad(step.pde_du(ur, mu), ur, g)
+    uv, ubuf = _embedded(u, offset)
+    nv, nbuf = _embedded(nn, offset)
+    gv, gbuf = _embedded(g, offset)
+    same(step.step_update(uv, mu, nv, om, os_), ref_upd, "update")
+    same(step.pde_du(uv, mu), ref_pde, "pde_du")
+    uvr = uv.detach().requires_grad_(True)
+    (gu,) = torch.autograd.grad(step.pde_du(uvr, mu), uvr, gv)
+    same(gu, ref_g, "adjoint")
+    # outputs written into guarded buffers
+    ov, obuf = _embedded(torch.zeros_like(u), offset)
+    from ppnn_b200 import _lib as L
+    step.step_update_(uv, mu, nv, L.f2(om), L.f2(os_), ov)
+    same(ov, ref_upd, "update into guarded buffer")
+    assert _guards_intact(ov, obuf)
+    for v, b in ((uv, ubuf), (nv, nbuf), (gv, gbuf)):
+        assert _guards_intact(v, b)
+    # fine solver (TMA-fed at 1025 wide, register kernel at 129)
+    for n in (1025, 129):
+        fb = pk["FineBurgers"]()
+        a = torch.rand(2, n, n, device="cuda", generator=gen) - 0.4
+        w = torch.rand(2, n, n, device="cuda", generator=gen) - 0.4
+        m2 = torch.tensor([0.03, 0.06], device="cuda")
+        r1, r2 = fb.step(a, w, m2)
+        av, abuf = _embedded(a, offset)
+        wv, wbuf = _embedded(w, offset)
+        o1, o1buf = _embedded(torch.zeros_like(a), offset)
+        o2, o2buf = _embedded(torch.zeros_like(a), offset)
+        fb.step_(av, wv, m2, o1, o2)
+        same(o1, r1, f"fine u {n} offset {offset}")
+        same(o2, r2, f"fine v {n} offset {offset}")
+        assert _guards_intact(o1, o1buf) and _guards_intact(o2, o2buf) and _guards_intact(av, abuf) and _guards_intact(wv, wbuf)

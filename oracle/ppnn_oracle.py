@@ -95,9 +95,19 @@ def upwind_taps(accuracy: int) -> Tuple[List[float], List[float]]:
 # --------------------------------------------------------------------------
 # Operators on pre-padded input (Tier A semantics).
 # --------------------------------------------------------------------------
+_KERNEL_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
 def _kernel(coeffs: Sequence[float], like: torch.Tensor, axis: int) -> torch.Tensor:
-    k = torch.tensor(list(coeffs), dtype=torch.float32).to(like.dtype)
-    return k.reshape(1, 1, -1, 1) if axis == 2 else k.reshape(1, 1, 1, -1)
+    """Filter tensor on the device / in the dtype of ``like`` (built once per combination,
+    as the reference builds its filters once per operator object, operators.py:145-222)."""
+    key = (tuple(coeffs), like.dtype, str(like.device), axis)
+    k = _KERNEL_CACHE.get(key)
+    if k is None:
+        k = torch.tensor(list(coeffs), dtype=torch.float32).to(device=like.device, dtype=like.dtype)
+        k = k.reshape(1, 1, -1, 1) if axis == 2 else k.reshape(1, 1, 1, -1)
+        _KERNEL_CACHE[key] = k
+    return k
 
 
 def correlate2d(u: torch.Tensor, coeffs: Sequence[float], axis: int) -> torch.Tensor:
@@ -106,7 +116,7 @@ def correlate2d(u: torch.Tensor, coeffs: Sequence[float], axis: int) -> torch.Te
 
 
 def correlate1d(u: torch.Tensor, coeffs: Sequence[float]) -> torch.Tensor:
-    k = torch.tensor(list(coeffs), dtype=torch.float32).to(u.dtype).reshape(1, 1, -1)
+    k = torch.tensor(list(coeffs), dtype=torch.float32).to(device=u.device, dtype=u.dtype).reshape(1, 1, -1)
     return F.conv1d(u, k)
 
 

@@ -95,6 +95,24 @@ def dev(t: torch.Tensor, what: str = "tensor") -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def on_device(t: torch.Tensor):
+    """Context that makes ``t``'s device current -- free when it already is."""
+    if t.device.index == torch.cuda.current_device():
+        return _NOCTX
+    return torch.cuda.device(t.device)
+
+
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 

@@ -49,33 +49,39 @@ def _taps(scheme_id: int, accuracy: int) -> int:
     return accuracy + 1                          # Forward1 / Backward1
 
 
+def _stencil_forward(u, scheme_id, accuracy, axis):
+    """Launch ``ppnn_stencil_fwd``; returns (output, contiguous input, (planes, hin, win))."""
+    lib = L.load()
+    x = L.dev(u, "operator input")
+    shape = x.shape
+    if x.dim() == 3:                         # 1-D operators: [B, 1, L]
+        if axis != 3:
+            raise RuntimeError("1-D operators act along the last dimension")
+        hin, win = 1, shape[-1]
+    else:
+        hin, win = shape[-2], shape[-1]
+    planes = x.numel() // (hin * win)
+    k = _taps(scheme_id, accuracy)
+    hout, wout = (hin - k + 1, win) if axis == 2 else (hin, win - k + 1)
+    if hout < 1 or wout < 1:
+        raise RuntimeError(f"input of shape {tuple(shape)} is smaller than the {k}-tap stencil")
+    out_shape = list(shape)
+    out_shape[-1] = wout
+    if axis == 2:
+        out_shape[-2] = hout
+    out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+    with L.on_device(x):
+        L.check(lib.ppnn_stencil_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, axis,
+                                     scheme_id, accuracy, L.stream()), "ppnn_stencil_fwd")
+    return out, x, (planes, hin, win)
+
+
 class _StencilFn(torch.autograd.Function):
     """y = valid cross-correlation of u with the (scheme, accuracy) filter along ``axis``."""
 
     @staticmethod
     def forward(ctx, u, scheme_id, accuracy, axis):
-        lib = L.load()
-        x = L.dev(u, "operator input")
-        shape = x.shape
-        if x.dim() == 3:                         # 1-D operators: [B, 1, L]
-            if axis != 3:
-                raise RuntimeError("1-D operators act along the last dimension")
-            hin, win = 1, shape[-1]
-        else:
-            hin, win = shape[-2], shape[-1]
-        planes = x.numel() // (hin * win)
-        k = _taps(scheme_id, accuracy)
-        hout, wout = (hin - k + 1, win) if axis == 2 else (hin, win - k + 1)
-        if hout < 1 or wout < 1:
-            raise RuntimeError(f"input of shape {tuple(shape)} is smaller than the {k}-tap stencil")
-        out_shape = list(shape)
-        out_shape[-1] = wout
-        if axis == 2:
-            out_shape[-2] = hout
-        out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            L.check(lib.ppnn_stencil_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, axis,
-                                         scheme_id, accuracy, L.stream()), "ppnn_stencil_fwd")
+        out, x, (planes, hin, win) = _stencil_forward(u, scheme_id, accuracy, axis)
         ctx.meta = (scheme_id, accuracy, axis, planes, hin, win)
         ctx.save_for_backward(x if scheme_id == L.UPWIND1 else None)
         return out
@@ -91,10 +97,17 @@ class _StencilFn(torch.autograd.Function):
         if axis == 2:
             shape[-2] = hin
         gin = torch.empty(shape, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with L.on_device(g):
             L.check(lib.ppnn_stencil_bwd(g.data_ptr(), L.ptr(x), gin.data_ptr(), planes, hin, win, axis,
                                          scheme_id, accuracy, L.stream()), "ppnn_stencil_bwd")
         return gin, None, None, None
+
+
+def _stencil(u, scheme_id, accuracy, axis):
+    """Operator call: straight to the kernel when no gradient can be needed."""
+    if isinstance(u, torch.Tensor) and not (torch.is_grad_enabled() and u.requires_grad):
+        return _stencil_forward(u, scheme_id, accuracy, axis)[0]
+    return _StencilFn.apply(u, scheme_id, accuracy, axis)
 
 
 def _resolve(table, scheme, accuracy):
@@ -134,7 +147,7 @@ class diffusion1D(operator_base1D):
         self._scheme_id = _resolve(_SCHEMES_1D, scheme, accuracy)
 
     def __call__(self, u: torch.Tensor) -> torch.Tensor:
-        return _StencilFn.apply(u, self._scheme_id, self.accuracy, 3)
+        return _stencil(u, self._scheme_id, self.accuracy, 3)
 
 
 class advection1d(operator_base1D):
@@ -161,7 +174,7 @@ class dudx_1D(operator_base1D):
         if self.scheme != 'Upwind':
             # the reference indexes the filter with ['forward'] and fails for other schemes
             raise TypeError("dudx_1D supports scheme='Upwind' only")
-        return _StencilFn.apply(u, self._scheme_id, self.accuracy, 3)
+        return _stencil(u, self._scheme_id, self.accuracy, 3)
 
 
 # --------------------------------------------------------------------------- 2-D
@@ -183,7 +196,7 @@ class operator_base2D(object):
     def _apply(self, u: torch.Tensor) -> torch.Tensor:
         if u.dim() != 4 or u.shape[1] != 1:
             raise RuntimeError(f"expected a [B,1,H,W] tensor, got {tuple(u.shape)}")
-        return _StencilFn.apply(u, self._scheme_id, self.accuracy, self._axis)
+        return _stencil(u, self._scheme_id, self.accuracy, self._axis)
 
 
 def _assert_second_derivative(scheme, accuracy):

@@ -135,22 +135,27 @@ def _mu_vector(mu, B, device):
     return torch.full((B,), float(mu), dtype=torch.float32, device=device)
 
 
+def _fused_forward(u1, v1, mu, ax, ay, rid, halo, adv, dif, scal):
+    lib = L.load()
+    B, _, H, W = u1.shape
+    u1c, v1c, axc, ayc = (L.dev(t) for t in (u1, v1, ax, ay))
+    muv = _mu_vector(mu, B, u1.device)
+    out = torch.empty_like(u1c)
+    dx, dy, dx2, dy2 = scal
+    with L.on_device(u1c):
+        L.check(lib.ppnn_rhs2d_fwd(u1c.data_ptr(), v1c.data_ptr(), muv.data_ptr(), axc.data_ptr(),
+                                   ayc.data_ptr(), out.data_ptr(), B, H, W, halo, rid,
+                                   adv[0], adv[1], dif[0], dif[1], dx, dy, dx2, dy2, L.stream()),
+                "ppnn_rhs2d_fwd")
+    return out, (u1c, v1c, muv, axc, ayc)
+
+
 class _FusedRhs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u1, v1, mu, ax, ay, rid, halo, adv, dif, scal):
-        lib = L.load()
-        B, _, H, W = u1.shape
-        u1c, v1c, axc, ayc = (L.dev(t) for t in (u1, v1, ax, ay))
-        muv = _mu_vector(mu, B, u1.device)
-        out = torch.empty_like(u1c)
-        dx, dy, dx2, dy2 = scal
-        with torch.cuda.device(u1.device):
-            L.check(lib.ppnn_rhs2d_fwd(u1c.data_ptr(), v1c.data_ptr(), muv.data_ptr(), axc.data_ptr(),
-                                       ayc.data_ptr(), out.data_ptr(), B, H, W, halo, rid,
-                                       adv[0], adv[1], dif[0], dif[1], dx, dy, dx2, dy2, L.stream()),
-                    "ppnn_rhs2d_fwd")
+        out, saved = _fused_forward(u1, v1, mu, ax, ay, rid, halo, adv, dif, scal)
         ctx.meta = (rid, halo, adv, dif, scal, isinstance(mu, torch.Tensor) and mu.shape)
-        ctx.save_for_backward(u1c, v1c, muv, axc, ayc)
+        ctx.save_for_backward(*saved)
         return out
 
     @staticmethod
@@ -200,8 +205,12 @@ def _make(name, rid):
         if plan is None:
             return _compose(rid, u1, v1, mu, dudx, dudy, d2udx2, d2udy2, ax, ay, dx, dy, dx2, dy2)
         halo, adv, dif = plan
-        return _FusedRhs.apply(u1, v1, mu, ax, ay, rid, halo, adv, dif,
-                               (float(dx), float(dy), float(dx2), float(dy2)))
+        scal = (float(dx), float(dy), float(dx2), float(dy2))
+        needs_grad = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad for t in (u1, v1, mu, ax, ay))
+        if not needs_grad:
+            return _fused_forward(u1, v1, mu, ax, ay, rid, halo, adv, dif, scal)[0]
+        return _FusedRhs.apply(u1, v1, mu, ax, ay, rid, halo, adv, dif, scal)
     f.__name__ = f.__qualname__ = name
     f.__doc__ = f"reference rhs.py `{name}`; ABI id {rid} (include/ppnn_b200.h)."
     return f

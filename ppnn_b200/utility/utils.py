@@ -30,18 +30,29 @@ def _hw(size: Size) -> Tuple[int, int]:
     return int(size), int(size)
 
 
+def _resample_forward(x, hout, wout, mode, align):
+    lib = L.load()
+    x = L.dev(x, "mesh_convertor input")
+    hin, win = x.shape[-2], x.shape[-1]
+    planes = x.numel() // (hin * win)
+    out = torch.empty(x.shape[:-2] + (hout, wout), dtype=torch.float32, device=x.device)
+    with L.on_device(x):
+        L.check(lib.ppnn_resample_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, hout, wout,
+                                      mode, int(align), L.stream()), "ppnn_resample_fwd")
+    return out, (planes, hin, win, hout, wout, mode, int(align), x.shape)
+
+
+def _resample(x, hout, wout, mode, align):
+    """mesh conversion: straight to the kernel when no gradient can be needed."""
+    if isinstance(x, torch.Tensor) and not (torch.is_grad_enabled() and x.requires_grad):
+        return _resample_forward(x, hout, wout, mode, align)[0]
+    return _ResampleFn.apply(x, hout, wout, mode, align)
+
+
 class _ResampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, hout, wout, mode, align):
-        lib = L.load()
-        x = L.dev(x, "mesh_convertor input")
-        hin, win = x.shape[-2], x.shape[-1]
-        planes = x.numel() // (hin * win)
-        out = torch.empty(x.shape[:-2] + (hout, wout), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            L.check(lib.ppnn_resample_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, hout, wout,
-                                          mode, int(align), L.stream()), "ppnn_resample_fwd")
-        ctx.meta = (planes, hin, win, hout, wout, mode, int(align), x.shape)
+        out, ctx.meta = _resample_forward(x, hout, wout, mode, align)
         return out
 
     @staticmethod
@@ -50,7 +61,7 @@ class _ResampleFn(torch.autograd.Function):
         planes, hin, win, hout, wout, mode, align, shape = ctx.meta
         g = L.dev(g, "mesh_convertor grad")
         gin = torch.empty(shape, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with L.on_device(g):
             L.check(lib.ppnn_resample_bwd(g.data_ptr(), gin.data_ptr(), planes, hin, win, hout, wout,
                                           mode, align, L.stream()), "ppnn_resample_bwd")
         return gin, None, None, None, None
@@ -76,13 +87,13 @@ class mesh_convertor(object):
         if u.dim() != 3:
             raise RuntimeError(f"dim=1 mesh_convertor expects [B,C,L], got {tuple(u.shape)}")
         size = self.cmesh_size[0] if isinstance(self.cmesh_size, (tuple, list)) else self.cmesh_size
-        return _ResampleFn.apply(u.unsqueeze(2), 1, int(size), L.BILINEAR, self.align_corners).squeeze(2)
+        return _resample(u.unsqueeze(2), 1, int(size), L.BILINEAR, self.align_corners).squeeze(2)
 
     def _downnd(self, u: torch.Tensor) -> torch.Tensor:
         if u.dim() != 4:
             raise RuntimeError(f"dim=2 mesh_convertor expects [B,C,H,W], got {tuple(u.shape)}")
         h, w = _hw(self.cmesh_size)
-        return _ResampleFn.apply(u, h, w, L.BILINEAR, self.align_corners)
+        return _resample(u, h, w, L.BILINEAR, self.align_corners)
 
     # -- up: interpolate(mode='bicubic', size=fmesh) ---------------------------
     def up1d(self, u: torch.Tensor) -> torch.Tensor:
@@ -94,11 +105,11 @@ class mesh_convertor(object):
         if u.shape[1] != 1:
             # with C > 1 rows the reference interpolates across channels too; keep that behaviour
             h, _ = _hw(self.fmesh_size)
-            return _ResampleFn.apply(u.unsqueeze(1), h, w, L.BICUBIC, self.align_corners)[:, :, 0]
-        return _ResampleFn.apply(u.unsqueeze(1), 1, w, L.BICUBIC, self.align_corners)[:, :, 0]
+            return _resample(u.unsqueeze(1), h, w, L.BICUBIC, self.align_corners)[:, :, 0]
+        return _resample(u.unsqueeze(1), 1, w, L.BICUBIC, self.align_corners)[:, :, 0]
 
     def upnd(self, u: torch.Tensor) -> torch.Tensor:
         if u.dim() != 4:
             raise RuntimeError(f"dim=2 mesh_convertor expects [B,C,H,W], got {tuple(u.shape)}")
         h, w = _hw(self.fmesh_size)
-        return _ResampleFn.apply(u, h, w, L.BICUBIC, self.align_corners)
+        return _resample(u, h, w, L.BICUBIC, self.align_corners)

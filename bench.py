@@ -320,7 +320,18 @@ def run_ours(args):
                                         gmu.data_ptr(), B, 1, L.stream()), "bwd")
         t = timed(adj, reps, 2)
         extras["step_adjoint"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
-        del gu, u_h, nn_h, out_h, dbuf
+        # training-set precompute (train2D.py:109-151): statistics pass and emit pass over (u, u_next) pairs
+        part = torch.empty(B, 2, 6, dtype=torch.float64, device=dev)
+        t = timed(lambda: L.check(lib.ppnn_dataset_stats(C.byref(step.cfg), u.data_ptr(), out.data_ptr(), muv.data_ptr(),
+                                                         B, 0, part.data_ptr(), L.stream()), "stats"), reps, 2)
+        extras["dataset_stats_pass"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
+        m6, s6 = (C.c_float * 6)(0, 0, 0, 0, 0, 0), (C.c_float * 6)(0.3, 0.3, 1e-3, 1e-3, 1e-3, 1e-3)
+        e1, e2 = torch.empty_like(nn), torch.empty_like(nn)
+        t = timed(lambda: L.check(lib.ppnn_dataset_emit(C.byref(step.cfg), u.data_ptr(), out.data_ptr(), muv.data_ptr(), B, 0,
+                                                        m6, s6, gu.data_ptr(), e1.data_ptr(), e2.data_ptr(), L.stream()),
+                                  "emit"), reps, 2)
+        extras["dataset_emit_pass"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 20, "hbm_gbs": 20 * pts / t / 1e6}
+        del gu, u_h, nn_h, out_h, dbuf, part, e1, e2
         # datagen (BASELINE config 4): fused Burgers step, 64 samples x 1025^2 per GPU
         fb = FineBurgers()
         n, bf = 1025, 64

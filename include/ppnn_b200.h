@@ -148,6 +148,28 @@ int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, const float* mu
 int ppnn_coarse_increment(const ppnn_coarse_cfg* cfg, const float* uc, const float* mu,
                           float* out, int B, int add_state, void* stream);
 
+/* Dataset-side precompute of the training set (src/train2D.py:88-90,109-151,
+ * class `myset`), device-resident.  Sample b is the pair (u, u_next) of states one
+ * step apart, both [*,2,FH,FW] fp32; traj_len = T > 0: the two arrays are views of
+ * one trajectory tensor [P,T+1,2,FH,FW] (u = its base, u_next = base + one state) and
+ * sample b sits at state slot b + b/T; traj_len = 0: dense arrays [B,2,FH,FW].
+ * With  pdeu = pde_du(u, mu)  and  label = (u_next - u) - pdeu :
+ *
+ * ppnn_dataset_stats  writes partial[B][2][6] (fp64): per (sample, channel) the sums
+ *   {u, u^2} over [:-1,:-1], {pdeu, pdeu^2} over the FULL plane (train2D.py:126-127
+ *   takes them before the crop), {label, label^2} over [:-1,:-1]; summed over B by the
+ *   caller, they give inmean/instd, pdemean/pdestd, outmean/outstd (:115-116,141-142).
+ * ppnn_dataset_emit   writes u0_normd, pdeu_normd, du_normd [B,2,FH-1,FW-1]
+ *   (:117,128,143); mean6 / std6 are HOST arrays {in c0,c1, pde c0,c1, out c0,c1}.
+ *
+ * Meshes the streamed kernel does not take (FW-1 not a multiple of 4, more than 512
+ * columns) return PPNN_E_SHAPE; compose from ppnn_pde_du_fwd in that case.          */
+int ppnn_dataset_stats(const ppnn_coarse_cfg* cfg, const float* u, const float* u_next, const float* mu,
+                       long B, long traj_len, double* partial, void* stream);
+int ppnn_dataset_emit(const ppnn_coarse_cfg* cfg, const float* u, const float* u_next, const float* mu,
+                      long B, long traj_len, const float* mean6, const float* std6,
+                      float* u_norm, float* pdeu_norm, float* label_norm, void* stream);
+
 /* ===================== Tier B: fine-grid explicit solver =================== */
 
 /* One explicit Euler step of the 2-D Burgers generator (src/operators.py:466-475)

@@ -36,7 +36,7 @@ parity, fp64 for the noise-floor reference).
 from __future__ import annotations
 
 from fractions import Fraction as Fr
-from typing import Callable, Dict, List, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -358,6 +358,36 @@ def ppnn_rollout(step: CoarseStep, net: Callable, u, mu, stats: Dict[str, torch.
             b = (mu - stats["mumean"]) / stats["mustd"]
             u = append_endpoint(net(a, b) * stats["outstd"] + stats["outmean"]) + u
         out.append(u)
+    return out
+
+
+def training_set(step: Optional["CoarseStep"], fdata: torch.Tensor, mus: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The data-set precompute of train2D.py:88-90 and class ``myset`` (:109-151).
+
+    ``fdata`` [P, T+1, 2, F, F] trajectories, ``mus`` [P*T, 1, 1, 1] one parameter per
+    sample; ``step`` None = the ``params.pde == False`` branch (:134-139).  Returns the
+    arrays and statistics the reference keeps as attributes of the data set."""
+    F = fdata.shape[-1]
+    data_u0 = fdata[:, :-1].reshape(-1, 2, F, F)                                  # :88
+    data_du = (fdata[:, 1:] - fdata[:, :-1]).reshape(-1, 2, F, F)                 # :89-90
+    out: Dict[str, torch.Tensor] = {}
+    out["inmean"] = data_u0[:, :, :-1, :-1].mean(dim=(0, 2, 3), keepdim=True)     # :115
+    out["instd"] = data_u0[:, :, :-1, :-1].std(dim=(0, 2, 3), keepdim=True)       # :116
+    out["u0_normd"] = (data_u0[:, :, :-1, :-1] - out["inmean"]) / out["instd"]    # :117
+    if step is not None:
+        pdeu = step.pde_du(data_u0, mus)                                          # :121
+        out["pdemean"] = pdeu.mean(dim=(0, 2, 3), keepdim=True)                   # :126 (full plane)
+        out["pdestd"] = pdeu.std(dim=(0, 2, 3), keepdim=True)                     # :127
+        out["pdeu_normd"] = (pdeu[:, :, :-1, :-1] - out["pdemean"]) / out["pdestd"]   # :128
+        du = (data_du - pdeu)[:, :, :-1, :-1]                                     # :129
+    else:
+        du = data_du[:, :, :-1, :-1]                                              # :137
+    out["outmean"] = du.mean(dim=(0, 2, 3), keepdim=True)                         # :144
+    out["outstd"] = du.std(dim=(0, 2, 3), keepdim=True)                           # :145
+    out["du_normd"] = (du - out["outmean"]) / out["outstd"]                       # :146
+    out["mumean"] = mus.mean()                                                    # :149
+    out["mustd"] = mus.std()                                                      # :150
+    out["mu_normd"] = (mus - mus.mean()) / mus.std()                              # :151
     return out
 
 

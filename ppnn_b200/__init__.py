@@ -20,3 +20,4 @@ from . import _lib  # noqa: F401
 from .fused import CoarseStep, FineBurgers, FineRhsSolver  # noqa: F401
 
 __all__ = ["CoarseStep", "FineBurgers", "FineRhsSolver", "operators", "rhs", "utility"]
+from .dataset import PdeDataset  # noqa: F401

@@ -51,6 +51,9 @@ _SIGNATURES = {
     "ppnn_step_update": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int, _P]),
     "ppnn_coarse_increment": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_int, C.c_int, _P]),
+    "ppnn_dataset_stats": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_long, C.c_long, _P, _P]),
+    "ppnn_dataset_emit": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_long, C.c_long,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P]),
     "ppnn_fine_burgers_step": (C.c_int, [_P] * 5 + [C.c_int] * 7 + [C.c_float] * 3 + [_P]),
     "ppnn_fine_rhs_step": (C.c_int, [_P] * 5 + [C.c_int] * 8 + [C.c_float] * 3 + [_P]),
 }

@@ -23,41 +23,6 @@
 // (F-1)/(C-1)-strided rows only (L2 hits).  No tensor cores: 1-channel 3..9-tap
 // stencils and a separable 4x4 interpolation have no dense contraction.
 #include <cstdlib>
-#include "coarse_common.cuh"
-
-namespace ppnn {
-
-enum { MODE_PDEU = 0, MODE_INPUTS = 1, MODE_UPDATE = 2 };
-
-struct StepIO {
-    const float* u;        // [B,2,FH,FW]
-    const float* mu;       // [B]
-    const float* nn;       // [B,2,FH-1,FW-1] or null          (MODE_UPDATE)
-    float* out;            // pdeu | u_next [B,2,FH,FW]        (may be null in MODE_INPUTS)
-    float* u_norm;         // [B,2,FH-1,FW-1]                  (MODE_INPUTS)
-    float* p_norm;         // [B,2,FH-1,FW-1] or null          (MODE_INPUTS)
-    float m0[2], s0[2];    // inmean/instd   (INPUTS) | outmean/outstd (UPDATE)
-    float m1[2], s1[2];    // pdemean/pdestd (INPUTS)
-};
-
-struct StepPlan {
-    int wmain;             // columns handled by strips (FW-1 when that is a multiple of 32, else FW)
-    int nchunk, nband, band_rows;
-};
-
-#ifndef PPNN_STEP_WARPS
-#define PPNN_STEP_WARPS 16
-#endif
-#ifndef PPNN_MINCTA
-#define PPNN_MINCTA 2
-#endif
-#ifndef PPNN_DEPTH
-#define PPNN_DEPTH 4
-#endif
-constexpr int kStepThreads = PPNN_STEP_WARPS * 32;
-constexpr int kDepth = PPNN_DEPTH;   // rows of streamed operands in flight per lane (register path)
-
-}  // namespace ppnn
 #include "coarse_step_staged.cuh"
 namespace ppnn {
 

@@ -17,7 +17,7 @@
 // tensor is clamped to its 16-byte-aligned end and the few trailing floats are
 // fetched with ordinary loads, so nothing outside the tensor is ever read.
 #pragma once
-#include "coarse_common.cuh"
+#include "coarse_step_types.cuh"
 #include "tma.cuh"
 
 namespace ppnn {
@@ -247,7 +247,12 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
 
     // ---- phase 3a: the duplicated-endpoint column, one point per thread --------
     const bool want_out = MODE == MODE_INPUTS ? io.out != nullptr : true;
-    if (pl.wmain < FW && want_out) {
+    // When the last fine column sits exactly on the last coarse node (always for 257 -> 33 / 49), its
+    // W-pass weights are (0,1,0,0) on the wrapped copy of coarse column 0, so pde(i, FW-1) is
+    // bit-identical to pde(i, 0): the lane that owns column 0 stores it from the ring (see row_out).
+    const float slast = p.suw * (float)(FW - 1);
+    const bool coldup = pl.wmain < FW && floorf(slast) == slast && ext_index((int)slast, p.CW) == 0;
+    if (pl.wmain < FW && want_out && !coldup) {
         const int jc = FW - 1;
         float wy[4]; int j0;
         cubic_entry(p.suw, jc, &j0, wy);
@@ -316,18 +321,25 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     const float4* wrow = roww + rs;
     const int* advp = rowadv + g * lay.nsteps;
 
+    const bool dupl = coldup && j == 0;                         // this lane also owns the duplicated endpoint column
     auto row_out = [&](int q, int row, int advbits, const float* su, const float* sn) {
         const float pde = prolong(wrow[q], (advbits >> q) & 1);
         if (MODE == MODE_PDEU) {
             if (active) st_stream(op + (size_t)q * FW, pde);
+            if (dupl) st_stream(op + (size_t)q * FW + PW, pde);
             return;
         }
         const float uu = su[q * FW];
         if (MODE == MODE_UPDATE) {
             const float v = HAS_NN ? (sn[q * PW] * s0 + m0) + uu + pde : uu + pde;
             if (active) st_stream(op + (size_t)q * FW, v);
+            if (dupl) {
+                const float ue = su[q * FW + PW];
+                st_stream(op + (size_t)q * FW + PW, HAS_NN ? (sn[q * PW] * s0 + m0) + ue + pde : ue + pde);
+            }
         } else {
             if (op && active) st_stream(op + (size_t)q * FW, pde);
+            if (op && dupl) st_stream(op + (size_t)q * FW + PW, pde);
             if (colok && row < PH) {
                 st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
                 if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));

@@ -245,6 +245,50 @@ def gen_pde_du():
     save("pde_du_65.npz", **out)
 
 
+# ---------------------------------------------------------------- training-set precompute
+def gen_dataset():
+    """train2D.py:88-90 and class myset (:109-151) executed line by line around the
+    imported reference modules, on two small synthetic trajectory sets."""
+    g = torch.Generator().manual_seed(1234)
+    P, T, F = 2, 3, 65
+    out = {}
+    for name in ("burgers_p", "rd_p"):
+        c = CASES[name]
+        cm = SMALL[name]
+        length = c["length"] * (cm - 1) / (c["cmesh"] - 1) * 0.5
+        pde_du, _ = make_pde_du(F, cm, c["rhsu"], c["rhsv"], c["dt"], length)
+        mu_p = torch.linspace(c["mu"][0], c["mu"][1], P)
+        w = torch.cat((fourier_field(g, P, F, 0.6), fourier_field(g, P, F, 0.6)), dim=1)
+        states = [w]
+        for _ in range(T):                     # a "fine solver" stand-in: coarse step + a smooth correction
+            corr = torch.cat((fourier_field(g, P, F, 0.6), fourier_field(g, P, F, 0.6)), dim=1)
+            w = w + pde_du(w, mu_p.reshape(-1, 1, 1, 1)) + 0.01 * corr
+            states.append(w)
+        fdata = torch.stack(states, dim=1).contiguous()            # [P, T+1, 2, F, F]
+        mus = mu_p.reshape(-1, 1).repeat(1, T).reshape(-1, 1, 1, 1)  # train2D.py `mus`: one per sample
+        feature_size = F
+        data_u0 = fdata[:, :-1].reshape(-1, 2, feature_size, feature_size)
+        data_du = (fdata[:, 1:] - fdata[:, :-1, ]).reshape(-1, 2, feature_size, feature_size)
+        inmean = data_u0[:, :, :-1, :-1].mean(dim=(0, 2, 3), keepdim=True)
+        instd = data_u0[:, :, :-1, :-1].std(dim=(0, 2, 3), keepdim=True)
+        u0_normd = (data_u0[:, :, :-1, :-1] - inmean) / instd
+        pdeu = pde_du(data_u0, mus)
+        pdemean = pdeu.mean(dim=(0, 2, 3), keepdim=True)
+        pdestd = pdeu.std(dim=(0, 2, 3), keepdim=True)
+        pdeu_normd = (pdeu[:, :, :-1, :-1] - pdemean) / pdestd
+        du = (data_du - pdeu)[:, :, :-1, :-1]
+        outmean = du.mean(dim=(0, 2, 3), keepdim=True)
+        outstd = du.std(dim=(0, 2, 3), keepdim=True)
+        du_normd = (du - outmean) / outstd
+        out.update({f"{name}/fdata": fdata, f"{name}/mus": mus, f"{name}/length": length,
+                    f"{name}/inmean": inmean, f"{name}/instd": instd, f"{name}/u0_normd": u0_normd,
+                    f"{name}/pdemean": pdemean, f"{name}/pdestd": pdestd, f"{name}/pdeu_normd": pdeu_normd,
+                    f"{name}/outmean": outmean, f"{name}/outstd": outstd, f"{name}/du_normd": du_normd,
+                    f"{name}/mumean": mus.mean(), f"{name}/mustd": mus.std(),
+                    f"{name}/mu_normd": (mus - mus.mean()) / mus.std()})
+    save("dataset_65.npz", **out)
+
+
 # ---------------------------------------------------------------- fine solver
 def gen_fine():
     """operators.py:416-420,450-455,466-475 around the imported modules."""
@@ -283,8 +327,7 @@ def gen_fine():
 
 
 if __name__ == "__main__":
-    gen_operators()
-    gen_rhs()
-    gen_mesh()
-    gen_pde_du()
-    gen_fine()
+    gens = dict(operators=gen_operators, rhs=gen_rhs, mesh=gen_mesh, pde_du=gen_pde_du, fine=gen_fine,
+                dataset=gen_dataset)
+    for which in (sys.argv[1:] or list(gens)):          # e.g. `make_golden.py dataset` regenerates one file
+        gens[which]()

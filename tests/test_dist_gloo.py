@@ -73,6 +73,35 @@ def _worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+def _stats_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ppnn_b200.dataset import finalize_stats
+        gen = torch.Generator().manual_seed(5)
+        x = torch.randn(3, 7, 2, 400, generator=gen) * torch.tensor([1.0, 3.0, 0.2]).reshape(3, 1, 1, 1) + 0.7
+        lo, hi = D.shard_bounds(7, rank, world)                 # ragged shards: 4 + 3 samples
+        xs = x[:, lo:hi].double()
+        sums = torch.stack((xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))), dim=-1)   # [3 stats, 2 ch, 2]
+        sums = sums.permute(1, 0, 2).reshape(2, 6)               # the kernel's [channel][6] layout
+        counts = torch.full((3,), float((hi - lo) * 400), dtype=torch.float64)
+        mean, std = finalize_stats(sums, counts)
+        ref_m = x.mean(dim=(1, 3))
+        ref_s = x.std(dim=(1, 3))
+        assert torch.allclose(mean, ref_m, rtol=1e-6, atol=1e-7) and torch.allclose(std, ref_s, rtol=1e-6)
+        if rank == 0:
+            open(os.path.join(tmp, "ok2"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dataset_statistics_all_reduce_gloo(tmp_path):
+    """Sharded training set: per-rank partial sums of ppnn_dataset_stats -> global mean / std."""
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_stats_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok2").read_text() == "ok"
+
+
 def test_world_size_2_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

@@ -610,3 +610,96 @@ def test_misaligned_and_end_of_allocation_buffers(pk, offset):
         same(o1, r1, f"fine u {n} offset {offset}")
         same(o2, r2, f"fine v {n} offset {offset}")
         assert _guards_intact(o1, o1buf) and _guards_intact(o2, o2buf) and _guards_intact(av, abuf) and _guards_intact(wv, wbuf)
+
+
+# ------------------------------------------------- training-set precompute
+def _assert_label_parity(ours, ref, outstd, pdeu):
+    """label = (u_next - u) - pdeu is a difference of nearly equal numbers, so its error is set by the
+    1e-5 parity of pdeu, not by its own (much smaller) magnitude: compare un-normalised, on pdeu's scale."""
+    err = ((ours - ref) * outstd).abs().amax(dim=(0, 2, 3))
+    scale = pdeu.abs().amax(dim=(0, 2, 3))
+    assert (err <= TOL * scale).all(), f"label error {err.tolist()} vs pdeu scale {scale.tolist()}"
+
+
+@pytest.mark.parametrize("case", ["burgers_p", "rd_p"])
+def test_dataset_precompute_against_reference_golden(pk, case):
+    """PdeDataset (ppnn_dataset_stats / ppnn_dataset_emit) vs train2D.py:88-151 run on the
+    reference modules (tests/golden/dataset_65.npz)."""
+    from ppnn_b200 import PdeDataset
+    g = load_golden("dataset_65.npz")
+    c = dict(burgers_p=("burgers2Dpu", "burgers2Dpv", 0.02, 9), rd_p=("rdpu", "rdpv", 0.002, 13))[case]
+    step = pk["CoarseStep"](65, c[3], c[0], c[1], c[2], float(g[f"{case}/length"]))
+    ds = PdeDataset(g[f"{case}/fdata"], g[f"{case}/mus"], step)
+    assert len(ds) == g[f"{case}/u0_normd"].shape[0]
+    for k in ("inmean", "instd", "pdemean", "pdestd", "outmean", "outstd"):
+        ref = g[f"{case}/{k}"]
+        scale = g[f"{case}/{k[:-4] if k.endswith('mean') else k[:-3]}std"]       # means are compared on the std scale
+        assert ((getattr(ds, k).cpu() - ref).abs() <= 1e-5 * scale.abs()).all(), k
+    for k in ("mumean", "mustd"):
+        assert torch.allclose(getattr(ds, k).cpu(), g[f"{case}/{k}"], rtol=1e-6)
+    for k in ("u0_normd", "pdeu_normd", "mu_normd"):
+        assert_parity(getattr(ds, k).cpu(), g[f"{case}/{k}"], TOL, f"{case}/{k}")
+    _assert_label_parity(ds.du_normd.cpu(), g[f"{case}/du_normd"], g[f"{case}/outstd"],
+                         g[f"{case}/pdeu_normd"] * g[f"{case}/pdestd"] + g[f"{case}/pdemean"])
+    u0, du, mu, pdeu = ds[1]
+    assert torch.equal(u0, ds.u0_normd[1]) and torch.equal(pdeu, ds.pdeu_normd[1]) and du.shape == (2, 64, 64)
+    seen = sum(b[0].shape[0] for b in ds.batches(4, shuffle=True))
+    assert seen == len(ds)
+
+
+def test_dataset_precompute_at_reference_mesh(pk):
+    """257/49 RD case, trajectories vs the oracle; dense (traj_len = 0) and trajectory
+    addressing of the C ABI give bit-identical partial sums; no-PDE branch."""
+    import ctypes as C
+    from ppnn_b200 import PdeDataset
+    L = pk["lib"]
+    gen = torch.Generator().manual_seed(77)
+    P, T, F = 3, 4, 257
+    ostep = O.CoarseStep(F, 49, "rdFu", "rdFv", 0.002, 6.4)
+    step = pk["CoarseStep"](F, 49, "rdFu", "rdFv", 0.002, 6.4)
+    w = torch.cat((O.fourier_initial_condition(torch.randn(P, 81, 2, generator=gen), F) - 0.6,
+                   O.fourier_initial_condition(torch.randn(P, 81, 2, generator=gen), F) - 0.6), dim=1)
+    mu_p = torch.linspace(0.2, 1.3, P)
+    states = [w]
+    for _ in range(T):
+        w = w + ostep.pde_du(w, mu_p.reshape(-1, 1, 1, 1)) + 1e-3 * torch.randn(P, 2, F, F, generator=gen)
+        states.append(w)
+    fdata = torch.stack(states, dim=1).contiguous()
+    mus = mu_p.reshape(-1, 1).repeat(1, T).reshape(-1, 1, 1, 1)
+    ref = O.training_set(ostep, fdata, mus)
+    ds = PdeDataset(fdata, mus, step, keep_trajectories=True)
+    for k in ("inmean", "pdemean", "outmean"):
+        s = ref[k[:-4] + "std"]
+        assert ((getattr(ds, k).cpu() - ref[k]).abs() <= 1e-5 * s).all(), k
+        assert torch.allclose(getattr(ds, k[:-4] + "std").cpu(), s, rtol=1e-5), k
+    for k in ("u0_normd", "pdeu_normd"):
+        assert_parity(getattr(ds, k).cpu(), ref[k], TOL, k)
+    _assert_label_parity(ds.du_normd.cpu(), ref["du_normd"], ref["outstd"],
+                         ref["pdeu_normd"] * ref["pdestd"] + ref["pdemean"])
+    # raw C ABI, dense addressing
+    lib = L.load()
+    B = P * T
+    u0 = fdata[:, :-1].reshape(B, 2, F, F).cuda().contiguous()
+    un = fdata[:, 1:].reshape(B, 2, F, F).cuda().contiguous()
+    muv = mus.reshape(-1).cuda().contiguous()
+    dense = torch.empty(B, 2, 6, dtype=torch.float64, device="cuda")
+    L.check(lib.ppnn_dataset_stats(C.byref(step.cfg), u0.data_ptr(), un.data_ptr(), muv.data_ptr(), B, 0,
+                                   dense.data_ptr(), L.stream()), "stats")
+    traj = ds.trajectories
+    tr = torch.empty_like(dense)
+    L.check(lib.ppnn_dataset_stats(C.byref(step.cfg), traj.data_ptr(), traj.reshape(-1)[2 * F * F:].data_ptr(),
+                                   muv.data_ptr(), B, T, tr.data_ptr(), L.stream()), "stats")
+    assert torch.equal(dense, tr)
+    pd = step.pde_du(u0, muv.reshape(-1, 1, 1, 1)).double()
+    assert torch.allclose(dense[:, :, 2], pd.sum(dim=(2, 3)), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(dense[:, :, 0], u0[:, :, :-1, :-1].double().sum(dim=(2, 3)), rtol=1e-6, atol=1e-5)
+    # error paths
+    assert lib.ppnn_dataset_stats(C.byref(step.cfg), None, un.data_ptr(), muv.data_ptr(), B, 0, dense.data_ptr(), L.stream()) == -1
+    odd = pk["CoarseStep"](63, 9, "rdpu", "rdpv", 0.002, 6.4)
+    assert lib.ppnn_dataset_stats(C.byref(odd.cfg), u0.data_ptr(), un.data_ptr(), muv.data_ptr(), 1, 0, dense.data_ptr(), L.stream()) == -2
+    # params.pde == False branch
+    ref0 = O.training_set(None, fdata, mus)
+    ds0 = PdeDataset(fdata, mus, None)
+    for k in ("u0_normd", "du_normd"):
+        assert_parity(getattr(ds0, k).cpu(), ref0[k], TOL, "nopde " + k)
+    assert len(ds0[0]) == 3

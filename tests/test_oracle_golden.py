@@ -139,3 +139,16 @@ def test_fourier_ic_range():
     f = O.fourier_initial_condition(coef, 33)
     assert f.shape == (2, 1, 33, 33)
     assert abs(f.min().item() - 0.1) < 1e-6 and abs(f.max().item() - 1.1) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["burgers_p", "rd_p"])
+def test_training_set_precompute(case):
+    """oracle.training_set against train2D.py:88-151 run on the reference modules."""
+    g = load_golden("dataset_65.npz")
+    c = CASES[case]
+    step = O.CoarseStep(65, SMALL[case], c["rhsu"], c["rhsv"], c["dt"], float(g[f"{case}/length"]))
+    out = O.training_set(step, g[f"{case}/fdata"], g[f"{case}/mus"])
+    for k in ("inmean", "instd", "pdemean", "pdestd", "outmean", "outstd", "mumean", "mustd"):
+        assert torch.allclose(out[k], g[f"{case}/{k}"], rtol=1e-6, atol=1e-9), k
+    for k in ("u0_normd", "pdeu_normd", "du_normd", "mu_normd"):
+        assert_parity(out[k], g[f"{case}/{k}"], 1e-6, f"{case}/{k}")

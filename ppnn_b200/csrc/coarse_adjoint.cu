@@ -312,6 +312,10 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
             const float* g_end = grad_out + (size_t)B * 2 * p.FH * p.FW;
+            if (a.gmu) {                                         // the two CTAs of a sample add their halves
+                e = cudaMemsetAsync(a.gmu, 0, (size_t)B * sizeof(float), (cudaStream_t)stream);
+                if (e != cudaSuccess) return (int)e;
+            }
             kern<<<2 * B, kAdjThreads, smem2, (cudaStream_t)stream>>>(p, a, lay, g_end);
             return launch_status();
         }

@@ -157,7 +157,13 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     // ---- phase 1a: the duplicated-endpoint column (one element per row) ------------------
     // base values point-wise; its H-pass as a gather per coarse row (fixed summation order,
     // so the result does not depend on thread scheduling)
-    if (!producer && lay.wmain < FW) {
+    // When the last fine column sits exactly on the last coarse node (257 -> 33 / 49), pde(i, FW-1)
+    // and pde(i, 0) are the same function of the coarse increment (see coarse_step_staged.cuh), so
+    // the lane that owns column 0 adds grad_out(i, FW-1) to its own cotangent straight from the
+    // ring and this point-wise phase is skipped; A[.][FW-1] then stays zero.
+    const float slast = p.suw * (float)(FW - 1);
+    const bool coldup = lay.wmain < FW && floorf(slast) == slast && ext_index((int)slast, p.CW) == 0;
+    if (!producer && lay.wmain < FW && !coldup) {
         const int jc = FW - 1;
         for (int i = tid; i < p.FH; i += kAdjWarps * 32)
             st_stream(of + (size_t)i * FW + jc, IDENT ? ld_stream(gf + (size_t)i * FW + jc) : 0.f);
@@ -214,16 +220,22 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             const int rr = (g == 1 && r - ovl_lo < 4) ? p.CH + (r - ovl_lo) : r;
             if (active) Af[rr * lay.apitch] += v;
         };
+        const bool dupl = coldup && j == 0;
         auto row_in = [&](int qq, int advbits, const float* sg) {
             if ((advbits >> qq) & 1) {                           // retire the oldest slot (warp-uniform)
                 flush(base - 1, c0);
                 c0 = c1; c1 = c2; c2 = c3; c3 = 0.f;
                 ++base;
             }
-            const float gv = sg[qq * FW];
+            float gv = sg[qq * FW];
+            if (active) st_stream(op + (size_t)qq * FW, IDENT ? gv : 0.f);
+            if (dupl) {
+                const float ge = sg[qq * FW + FW - 1];
+                st_stream(op + (size_t)qq * FW + FW - 1, IDENT ? ge : 0.f);
+                gv += ge;
+            }
             const float4 wx = wrow[qq];
             c0 += wx.x * gv; c1 += wx.y * gv; c2 += wx.z * gv; c3 += wx.w * gv;
-            if (active) st_stream(op + (size_t)qq * FW, IDENT ? gv : 0.f);
         };
         for (int t = 0; t < lay.nsteps; ++t) {
             const int s = t % kAdjStages;
@@ -272,6 +284,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
                 int I = ei ? p.NH : Ip;
                 const float* row = A + I * lay.apitch + js;
                 float t = 0.f;
+#pragma unroll 4
                 for (int k = 0; k < cnt; ++k) t += w[k] * row[k];
                 sum += t;
             }
@@ -279,13 +292,40 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         q[Ip * p.NW + Jp] = p.dt * sum;
     }
     {
+        // all loads of a batch of coarse points in flight at once (as the forward kernel's phase 1)
+        constexpr int GB = 5;
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-#pragma unroll 4
-        for (int idx = lo + tid; idx < hi; idx += nthr) {
-            int g = idx >= nn2;
-            int r = idx - g * nn2;
-            int I = r / p.NW, J = r - I * p.NW;
-            cu[idx] = restrict_point(p, ub + g * plane, I, J);
+        for (int i0 = lo + tid; i0 < hi; i0 += GB * nthr) {
+            float va[GB], vb[GB], vc[GB], vd[GB];
+            BilinearTap tp[GB];
+#pragma unroll
+            for (int k = 0; k < GB; ++k) {
+                const int idx = i0 + k * nthr;
+                va[k] = vb[k] = vc[k] = vd[k] = 0.f;
+                if (idx < hi) {
+                    const int g = idx >= nn2;
+                    const int r = idx - g * nn2;
+                    const int I = r / p.NW, J = r - I * p.NW;
+                    tp[k] = bilinear_tap(p, I, J);
+                    const float* src = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
+                    va[k] = __ldg(src);
+                    if (tp[k].lj != 0.f) vb[k] = __ldg(src + tp[k].dj);
+                    if (tp[k].li != 0.f) {
+                        const float* r2 = src + (size_t)tp[k].di * FW;
+                        vc[k] = __ldg(r2);
+                        if (tp[k].lj != 0.f) vd[k] = __ldg(r2 + tp[k].dj);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < GB; ++k) {
+                const int idx = i0 + k * nthr;
+                if (idx < hi) {
+                    const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
+                    const float top = w0 * va[k] + tp[k].lj * vb[k];
+                    cu[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * vc[k] + tp[k].lj * vd[k]);
+                }
+            }
         }
     }
     // grad_mu partial of this field (needs only local data)
@@ -308,12 +348,22 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         if (lane == 0) mu_partial = v;
     }
 
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();               // q and mu_partial of both CTAs are complete
+    // grad_mu[b] = partial(u) + partial(v): the launcher zeroed it; a sum of two floats does not depend on order
+    if (tid == 0 && a.gmu) atomicAdd(a.gmu + b, mu_partial);
+
+    // ---- exchange of the coarse cotangents (only when a right-hand side couples the fields) ----
+    // The peer's q is copied into A (dead after the W-pass) between two back-to-back cluster barriers,
+    // so that phases 3 and 4 run, and the CTAs retire, independently of each other.
+    const float* q_oth = A;
+    if (both) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                           // q of both CTAs complete
+        const float* q_peer = cluster.map_shared_rank(q, f ^ 1);
+        for (int idx = tid; idx < nn2; idx += nthr) A[idx] = q_peer[idx];
+        cluster.sync();                                           // both are done reading each other
+    }
 
     // ---- phase 3 + 4: own field's coarse cotangent, scatter through D_down^T ------
-    const float* q_oth = cluster.map_shared_rank(q, f ^ 1);
-    if (f == 0 && tid == 0 && a.gmu) a.gmu[b] = mu_partial + *cluster.map_shared_rank(&mu_partial, 1);
     for (int idx = tid; idx < nn2; idx += nthr) {
         int I = idx / p.NW, J = idx - I * p.NW;
         const float q_own = q[idx];
@@ -348,7 +398,6 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             if (t.lj != 0.f) atomicAdd(o2 + t.dj, t.li * t.lj * cot);
         }
     }
-    cluster.sync();               // the peer may still be reading this CTA's shared memory
 }
 
 }  // namespace ppnn

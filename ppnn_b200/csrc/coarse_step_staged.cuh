@@ -347,26 +347,38 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         }
     };
 
-    for (int t = 0; t < lay.nsteps; ++t) {
-        const int s = t % kStages;
-        const int r0 = rs + t * kStageRows;
-        const float* su = su_base + (size_t)s * 2 * lay.ustage;
-        const float* sn = sn_base + (size_t)s * 2 * lay.nstage;
-        const int advbits = advp[t];
-        if (MODE != MODE_PDEU) mbar_wait(&full[s], (t / kStages) & 1);
-        if (r0 + kStageRows <= re) {
-#pragma unroll
-            for (int q = 0; q < kStageRows; ++q) row_out(q, r0 + q, advbits, su, sn);
-        } else {
-            for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sn);   // ragged last band
-        }
+    // ring position kept incrementally; barrier addresses converted to the shared window once
+    const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+    const size_t ustep = (size_t)2 * lay.ustage, nstep = (size_t)2 * lay.nstage;
+    const float* su = su_base;
+    const float* sn = sn_base;
+    int s = 0; uint32_t ph = 0;
+    const int nfull = (re - rs) / kStageRows;                   // whole bands of this row group
+    auto advance = [&]() {
         if (MODE != MODE_PDEU) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done with slot s
+            if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);  // this warp is done with slot s
+            if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
+            else { su += ustep; sn += nstep; }
         }
         wrow += kStageRows;
         if (op) op += (size_t)kStageRows * FW;
         if (MODE == MODE_INPUTS) { unp += (size_t)kStageRows * PW; if (pnp) pnp += (size_t)kStageRows * PW; }
+    };
+    int t = 0;
+    for (; t < nfull; ++t) {
+        const int advbits = advp[t];
+        if (MODE != MODE_PDEU) mbar_wait_addr(full_a + 8u * s, ph);
+#pragma unroll
+        for (int q = 0; q < kStageRows; ++q) row_out(q, rs + t * kStageRows + q, advbits, su, sn);
+        advance();
+    }
+    for (; t < lay.nsteps; ++t) {                               // ragged last band; steps only the other group has
+        const int r0 = rs + t * kStageRows;
+        const int advbits = advp[t];
+        if (MODE != MODE_PDEU) mbar_wait_addr(full_a + 8u * s, ph);
+        for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sn);
+        advance();
     }
 }
 

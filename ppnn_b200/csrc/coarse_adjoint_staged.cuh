@@ -237,22 +237,32 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             const float4 wx = wrow[qq];
             c0 += wx.x * gv; c1 += wx.y * gv; c2 += wx.z * gv; c3 += wx.w * gv;
         };
-        for (int t = 0; t < lay.nsteps; ++t) {
-            const int s = t % kAdjStages;
-            const int r0 = rs + t * R;
-            const float* sg = sg_base + (size_t)s * 2 * lay.gstage;
-            const int advbits = advp[t];
-            mbar_wait(&full[s], (t / kAdjStages) & 1);
-            if (r0 + R <= re) {
-#pragma unroll
-                for (int qq = 0; qq < R; ++qq) row_in(qq, advbits, sg);
-            } else {
-                for (int qq = 0; r0 + qq < re; ++qq) row_in(qq, advbits, sg);     // ragged last band
-            }
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const size_t gstep = (size_t)2 * lay.gstage;
+        const float* sg = sg_base;
+        int s = 0; uint32_t ph = 0;
+        const int nfull = (re - rs) / R;
+        auto advance = [&]() {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
+            if (++s == kAdjStages) { s = 0; ph ^= 1u; sg = sg_base; } else { sg += gstep; }
             wrow += R;
             op += (size_t)R * FW;
+        };
+        int t = 0;
+        for (; t < nfull; ++t) {
+            const int advbits = advp[t];
+            mbar_wait_addr(full_a + 8u * s, ph);
+#pragma unroll
+            for (int qq = 0; qq < R; ++qq) row_in(qq, advbits, sg);
+            advance();
+        }
+        for (; t < lay.nsteps; ++t) {                            // ragged last band; steps only the other group has
+            const int r0 = rs + t * R;
+            const int advbits = advp[t];
+            mbar_wait_addr(full_a + 8u * s, ph);
+            for (int qq = 0; r0 + qq < re; ++qq) row_in(qq, advbits, sg);
+            advance();
         }
         flush(base - 1, c0); flush(base, c1); flush(base + 1, c2); flush(base + 2, c3);
     }

@@ -296,23 +296,34 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
             }
         };
 
-        for (int t = 0; t < lay.nsteps; ++t) {
-            const int s = t % kStages;
-            const int r0 = rs + t * kStageRows;
-            const float* su = su_base + (size_t)s * 2 * lay.ustage;
-            const float* sx = sx_base + (size_t)s * 2 * lay.ustage;
-            const int advbits = advp[t];
-            mbar_wait(&full[s], (t / kStages) & 1);
-            if (r0 + kStageRows <= re) {
-#pragma unroll
-                for (int q = 0; q < kStageRows; ++q) row_out(q, r0 + q, advbits, su, sx);
-            } else {
-                for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sx);
-            }
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const size_t ustep = (size_t)2 * lay.ustage;
+        const float* su = su_base;
+        const float* sx = sx_base;
+        int s = 0; uint32_t ph = 0;
+        const int nfull = (re - rs) / kStageRows;
+        auto advance = [&]() {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
+            if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
+            else { su += ustep; sx += ustep; }
             wrow += kStageRows;
             if (EMIT) { unp += (size_t)kStageRows * PW; pnp += (size_t)kStageRows * PW; lnp += (size_t)kStageRows * PW; }
+        };
+        int t = 0;
+        for (; t < nfull; ++t) {
+            const int advbits = advp[t];
+            mbar_wait_addr(full_a + 8u * s, ph);
+#pragma unroll
+            for (int q = 0; q < kStageRows; ++q) row_out(q, rs + t * kStageRows + q, advbits, su, sx);
+            advance();
+        }
+        for (; t < lay.nsteps; ++t) {
+            const int r0 = rs + t * kStageRows;
+            const int advbits = advp[t];
+            mbar_wait_addr(full_a + 8u * s, ph);
+            for (int q = 0; r0 + q < re; ++q) row_out(q, r0 + q, advbits, su, sx);
+            advance();
         }
     }
 

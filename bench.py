@@ -408,7 +408,7 @@ def run_ours(args):
                            "8 chunks over 2 streams"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "coarse_step_kernel<MODE_UPDATE>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "coarse_step_staged_kernel<MODE_UPDATE, 257, HAS_NN>",
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT * pts,
                          "bytes_per_point_update": BYTES_PER_POINT},
             "extras": extras}

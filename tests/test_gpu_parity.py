@@ -703,3 +703,56 @@ def test_dataset_precompute_at_reference_mesh(pk):
     for k in ("u0_normd", "du_normd"):
         assert_parity(getattr(ds0, k).cpu(), ref0[k], TOL, "nopde " + k)
     assert len(ds0[0]) == 3
+
+
+# ------------------------------------------------- other mesh shapes: every kernel-selection branch
+@pytest.mark.parametrize("fine,coarse,rhs", [
+    (97, 33, ("burgers2DFu", "burgers2DFv")),     # staged kernel, last column NOT on a coarse node in fp32 (32/96): point-wise column
+    (129, 33, ("rdFu", "rdFv")),                  # staged kernel, dyadic ratio: column taken from the ring
+    (49, 13, ("burgers2Dpu", "burgers2Dpv")),     # staged kernel, width not a multiple of 32 + 1: no special column
+    (63, 9, ("rdpu", "rdpv")),                    # (F-1) % 4 != 0: register fallback kernel
+    ((81, 129), (21, 33), ("burgers2Dpu", "burgers2Dpv")),   # non-square
+])
+def test_coarse_step_other_meshes(pk, fine, coarse, rhs):
+    fh, fw = (fine, fine) if isinstance(fine, int) else fine
+    ch, cw = (coarse, coarse) if isinstance(coarse, int) else coarse
+    gen = torch.Generator().manual_seed(1000 * fh + ch)
+    B = 5
+    dt, length = 0.004, 1.6
+    step = pk["CoarseStep"](fine, coarse, rhs[0], rhs[1], dt, length)
+    ostep = O.CoarseStep(fine, coarse, rhs[0], rhs[1], dt, length) if isinstance(fine, int) else None
+    u = torch.randn(B, 2, fh, fw, generator=gen) * 0.5
+    mu = torch.linspace(0.02, 0.4, B).reshape(-1, 1, 1, 1)
+    nn_out = torch.randn(B, 2, fh - 1, fw - 1, generator=gen)
+    om, osd = torch.tensor([0.01, -0.02]).reshape(1, 2, 1, 1), torch.tensor([0.3, 0.2]).reshape(1, 2, 1, 1)
+    if ostep is None:
+        # non-square: the oracle class is square-only; compose the reference op sequence here
+        def ref_pde_du(x, m):
+            u1 = O.mesh_down(x[:, :1], (ch, cw))[:, :, :-1, :-1]
+            v1 = O.mesh_down(x[:, 1:], (ch, cw))[:, :, :-1, :-1]
+            ops = O.Ops(1, 2)
+            dx = length / (ch - 1)
+            ru = O.rhs(rhs[0], u1, v1, m, ops, O.wrap_x(u1), O.wrap_y(u1), dx, dx, dx * dx, dx * dx)
+            rv = O.rhs(rhs[1], u1, v1, m, ops, O.wrap_x(v1), O.wrap_y(v1), dx, dx, dx * dx, dx * dx)
+            return torch.cat((O.mesh_up(O.append_endpoint(dt * ru), (fh, fw)),
+                              O.mesh_up(O.append_endpoint(dt * rv), (fh, fw))), dim=1)
+    else:
+        ref_pde_du = ostep.pde_du
+    ur = u.clone().requires_grad_(True)
+    mr = mu.clone().requires_grad_(True)
+    ref = ref_pde_du(ur, mr)
+    cot = torch.randn(B, 2, fh, fw, generator=gen)
+    gu_ref, gm_ref = torch.autograd.grad(ref, (ur, mr), cot, allow_unused=True)
+    uc = u.cuda().requires_grad_(True)
+    mc = mu.cuda().requires_grad_(True)
+    ours = step.pde_du(uc, mc)
+    assert_parity(ours.detach().cpu(), ref.detach(), TOL, "pde_du")
+    gu, gm = torch.autograd.grad(ours, (uc, mc), cot.cuda(), allow_unused=True)
+    assert_parity(gu.cpu(), gu_ref, TOL, "grad_u")
+    if gm_ref is not None and gm_ref.abs().max() > 0:
+        assert_parity(gm.cpu(), gm_ref, 5e-5, "grad_mu")
+    upd = step.step_update(u.cuda(), mu.cuda(), nn_out.cuda(), om.cuda(), osd.cuda())
+    assert_parity(upd.cpu(), O.ppnn_update(u, ref.detach(), nn_out, om, osd), TOL, "update")
+    a, pn = step.step_inputs(u.cuda(), mu.cuda(), om.cuda(), osd.cuda(), om.cuda(), osd.cuda() * 1e-2)[:2]
+    assert_parity(a.cpu(), (u[:, :, :-1, :-1] - om) / osd, TOL, "u_norm")
+    assert_parity(pn.cpu(), (ref.detach()[:, :, :-1, :-1] - om) / (osd * 1e-2), TOL, "pdeu_norm")

@@ -23,8 +23,7 @@
 //            into the CTA's own plane (after its own base values, same CTA => ordered)
 #pragma once
 #include <cooperative_groups.h>
-#include "coarse_common.cuh"
-#include "tma.cuh"
+#include "coarse_step_staged.cuh"
 
 namespace ppnn {
 
@@ -115,22 +114,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         }
     } else {
         // tables and a cleared accumulator while the first bands fly
-        for (int i = tid; i < p.FH; i += kAdjWarps * 32) {
-            float w[4]; int i0;
-            cubic_entry(p.suh, i, &i0, w);
-            rowi[i] = i0;
-            roww[i] = make_float4(w[0], w[1], w[2], w[3]);
-        }
-        for (int e = tid; e < 2 * lay.nsteps; e += kAdjWarps * 32) {
-            const int g = e >= lay.nsteps, t = e - g * lay.nsteps;
-            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
-            int bits = 0;
-            for (int qq = 0; qq < R; ++qq) {
-                const int i = rs + t * R + qq;
-                if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << qq;
-            }
-            rowadv[e] = bits;
-        }
+        build_row_tables(p, lay.split, lay.nsteps, R, roww, rowi, rowadv, tid, kAdjWarps * 32);
         for (int J = tid; J < p.CW; J += kAdjWarps * 32) {
             int js = (int)ceilf((float)(J - 2) / p.suw) - 1;
             jstart[J] = js < 0 ? 0 : js;
@@ -302,41 +286,9 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
         q[Ip * p.NW + Jp] = p.dt * sum;
     }
     {
-        // all loads of a batch of coarse points in flight at once (as the forward kernel's phase 1)
-        constexpr int GB = 5;
+        // (u is not streamed by this kernel: no L2 retention hint)
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-        for (int i0 = lo + tid; i0 < hi; i0 += GB * nthr) {
-            float va[GB], vb[GB], vc[GB], vd[GB];
-            BilinearTap tp[GB];
-#pragma unroll
-            for (int k = 0; k < GB; ++k) {
-                const int idx = i0 + k * nthr;
-                va[k] = vb[k] = vc[k] = vd[k] = 0.f;
-                if (idx < hi) {
-                    const int g = idx >= nn2;
-                    const int r = idx - g * nn2;
-                    const int I = r / p.NW, J = r - I * p.NW;
-                    tp[k] = bilinear_tap(p, I, J);
-                    const float* src = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
-                    va[k] = __ldg(src);
-                    if (tp[k].lj != 0.f) vb[k] = __ldg(src + tp[k].dj);
-                    if (tp[k].li != 0.f) {
-                        const float* r2 = src + (size_t)tp[k].di * FW;
-                        vc[k] = __ldg(r2);
-                        if (tp[k].lj != 0.f) vd[k] = __ldg(r2 + tp[k].dj);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < GB; ++k) {
-                const int idx = i0 + k * nthr;
-                if (idx < hi) {
-                    const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
-                    const float top = w0 * va[k] + tp[k].lj * vb[k];
-                    cu[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * vc[k] + tp[k].lj * vd[k]);
-                }
-            }
-        }
+        gather_coarse<false>(p, ub, plane, FW, lo, hi, cu, tid, nthr);
     }
     // grad_mu partial of this field (needs only local data)
     __syncthreads();

@@ -128,55 +128,8 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         // ---- phase 1: restriction gather + row tables (as coarse_step_staged_kernel) ----
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-        const uint64_t pol_keep = l2_policy_evict_last();
-        for (int i0 = lo + tid; i0 < hi; i0 += kGatherBatch * kStepThreads) {
-            float a[kGatherBatch], bq[kGatherBatch], c[kGatherBatch], d[kGatherBatch];
-            BilinearTap tp[kGatherBatch];
-#pragma unroll
-            for (int k = 0; k < kGatherBatch; ++k) {
-                const int idx = i0 + k * kStepThreads;
-                a[k] = bq[k] = c[k] = d[k] = 0.f;
-                if (idx < hi) {
-                    const int g = idx >= nn2;
-                    const int r = idx - g * nn2;
-                    const int I = r / p.NW, J = r - I * p.NW;
-                    tp[k] = bilinear_tap(p, I, J);
-                    const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
-                    a[k] = ld_hint(q, pol_keep);
-                    if (tp[k].lj != 0.f) bq[k] = ld_hint(q + tp[k].dj, pol_keep);
-                    if (tp[k].li != 0.f) {
-                        const float* r2 = q + (size_t)tp[k].di * FW;
-                        c[k] = ld_hint(r2, pol_keep);
-                        if (tp[k].lj != 0.f) d[k] = ld_hint(r2 + tp[k].dj, pol_keep);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kGatherBatch; ++k) {
-                const int idx = i0 + k * kStepThreads;
-                if (idx < hi) {
-                    const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
-                    const float top = w0 * a[k] + tp[k].lj * bq[k];
-                    cu[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * c[k] + tp[k].lj * d[k]);
-                }
-            }
-        }
-        for (int i = tid; i < p.FH; i += kStepThreads) {
-            float w[4]; int i0;
-            cubic_entry(p.suh, i, &i0, w);
-            rowi[i] = i0;
-            roww[i] = make_float4(w[0], w[1], w[2], w[3]);
-        }
-        for (int e = tid; e < 2 * lay.nsteps; e += kStepThreads) {
-            const int g = e >= lay.nsteps, t = e - g * lay.nsteps;
-            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
-            int bits = 0;
-            for (int q = 0; q < kStageRows; ++q) {
-                const int i = rs + t * kStageRows + q;
-                if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
-            }
-            rowadv[e] = bits;
-        }
+        gather_coarse<true>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
+        build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
 

@@ -69,6 +69,75 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
+constexpr int kGatherBatch = 5;                     // coarse points per thread whose loads are issued together
+
+// Bilinear restriction gather (mesh_convertor.down + [:, :, :-1, :-1]) of the coarse points
+// [lo, hi) of the index space [field][I][J] into dst[idx], by `nthr` threads: the up-to-4 taps
+// of kGatherBatch points per thread are all in flight before the first is used; zero-weight
+// taps are skipped (exact decimation for 257 -> 33).  KEEP: tag the loads L2::evict_last
+// because the same sectors are streamed again a few microseconds later.
+template <bool KEEP>
+__device__ __forceinline__ void gather_coarse(const CoarseParams& p, const float* __restrict__ ub, size_t plane, int FW,
+                                              int lo, int hi, float* dst, int tid, int nthr) {
+    const int nn2 = p.NH * p.NW;
+    const uint64_t pol_keep = KEEP ? l2_policy_evict_last() : 0;
+    auto ld = [&](const float* q) -> float { return KEEP ? ld_hint(q, pol_keep) : __ldg(q); };
+    for (int i0 = lo + tid; i0 < hi; i0 += kGatherBatch * nthr) {
+        float a[kGatherBatch], bq[kGatherBatch], c[kGatherBatch], d[kGatherBatch];
+        BilinearTap tp[kGatherBatch];
+#pragma unroll
+        for (int k = 0; k < kGatherBatch; ++k) {
+            const int idx = i0 + k * nthr;
+            a[k] = bq[k] = c[k] = d[k] = 0.f;
+            if (idx < hi) {
+                const int g = idx >= nn2;
+                const int r = idx - g * nn2;
+                const int I = r / p.NW, J = r - I * p.NW;
+                tp[k] = bilinear_tap(p, I, J);
+                const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
+                a[k] = ld(q);
+                if (tp[k].lj != 0.f) bq[k] = ld(q + tp[k].dj);
+                if (tp[k].li != 0.f) {
+                    const float* r2 = q + (size_t)tp[k].di * FW;
+                    c[k] = ld(r2);
+                    if (tp[k].lj != 0.f) d[k] = ld(r2 + tp[k].dj);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kGatherBatch; ++k) {
+            const int idx = i0 + k * nthr;
+            if (idx < hi) {
+                const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
+                const float top = w0 * a[k] + tp[k].lj * bq[k];
+                dst[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * c[k] + tp[k].lj * d[k]);
+            }
+        }
+    }
+}
+
+// Per-CTA tables of the prolongation: H-pass weights and source row of every fine row, and per
+// ring step a bit mask "row q of this band moves the 4-row coarse window on" for both row groups.
+__device__ __forceinline__ void build_row_tables(const CoarseParams& p, int split, int nsteps, int rows_per_step,
+                                                 float4* roww, int* rowi, int* rowadv, int tid, int nthr) {
+    for (int i = tid; i < p.FH; i += nthr) {
+        float w[4]; int i0;
+        cubic_entry(p.suh, i, &i0, w);
+        rowi[i] = i0;
+        roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    for (int e = tid; e < 2 * nsteps; e += nthr) {
+        const int g = e >= nsteps, t = e - g * nsteps;
+        const int rs = g ? split : 0, re = g ? p.FH : split;
+        int bits = 0;
+        for (int q = 0; q < rows_per_step; ++q) {
+            const int i = rs + t * rows_per_step + q;
+            if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
+        }
+        rowadv[e] = bits;
+    }
+}
+
 struct StagedLayout {
     int ustage;      // floats per (stage, group) u buffer: kStageRows*FW + 8 (lead / tail slack), 16 B multiple
     int nstage;      // floats per (stage, group) nn buffer: kStageRows*PW
@@ -78,8 +147,6 @@ struct StagedLayout {
 
 
 constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 producer warp
-constexpr int kGatherBatch = 5;                     // coarse points per thread whose loads are issued together
-
 // One CTA = one (sample, field) plane.  Consumer warp = (row group g, 32-column
 // chunk): group 0 walks rows [0, split), group 1 rows [split, FH), both fed by
 // the same ring step.  HAS_NN: the update adds the network output (MODE_UPDATE).
@@ -162,55 +229,8 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         // a purely diffusive right-hand side never reads the other field
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-        const uint64_t pol_keep = l2_policy_evict_last();
-        for (int i0 = lo + tid; i0 < hi; i0 += kGatherBatch * kStepThreads) {
-            float a[kGatherBatch], bq[kGatherBatch], c[kGatherBatch], d[kGatherBatch];
-            BilinearTap tp[kGatherBatch];
-#pragma unroll
-            for (int k = 0; k < kGatherBatch; ++k) {
-                const int idx = i0 + k * kStepThreads;
-                a[k] = bq[k] = c[k] = d[k] = 0.f;
-                if (idx < hi) {
-                    const int g = idx >= nn2;
-                    const int r = idx - g * nn2;
-                    const int I = r / p.NW, J = r - I * p.NW;
-                    tp[k] = bilinear_tap(p, I, J);
-                    const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
-                    a[k] = ld_hint(q, pol_keep);
-                    if (tp[k].lj != 0.f) bq[k] = ld_hint(q + tp[k].dj, pol_keep);
-                    if (tp[k].li != 0.f) {
-                        const float* r2 = q + (size_t)tp[k].di * FW;
-                        c[k] = ld_hint(r2, pol_keep);
-                        if (tp[k].lj != 0.f) d[k] = ld_hint(r2 + tp[k].dj, pol_keep);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kGatherBatch; ++k) {
-                const int idx = i0 + k * kStepThreads;
-                if (idx < hi) {
-                    const float h0 = 1.f - tp[k].li, w0 = 1.f - tp[k].lj;
-                    const float top = w0 * a[k] + tp[k].lj * bq[k];
-                    cu[idx] = tp[k].li == 0.f ? h0 * top : h0 * top + tp[k].li * (w0 * c[k] + tp[k].lj * d[k]);
-                }
-            }
-        }
-        for (int i = tid; i < p.FH; i += kStepThreads) {
-            float w[4]; int i0;
-            cubic_entry(p.suh, i, &i0, w);
-            rowi[i] = i0;
-            roww[i] = make_float4(w[0], w[1], w[2], w[3]);
-        }
-        for (int e = tid; e < 2 * lay.nsteps; e += kStepThreads) {
-            const int g = e >= lay.nsteps, t = e - g * lay.nsteps;
-            const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
-            int bits = 0;
-            for (int q = 0; q < kStageRows; ++q) {
-                const int i = rs + t * kStageRows + q;
-                if (i > rs && i < re && floorf(p.suh * (float)i) != floorf(p.suh * (float)(i - 1))) bits |= 1 << q;
-            }
-            rowadv[e] = bits;
-        }
+        gather_coarse<true>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
+        build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
 

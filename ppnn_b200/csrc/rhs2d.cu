@@ -3,6 +3,7 @@
 // train2D.py:75-77 and operators.py:474-475 compute with ~30 ATen launches.
 // 20 B per output point (u1, v1, ax, ay read, out written).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ppnn {
 
@@ -13,6 +14,7 @@ struct RhsParams {
     int rhs_id, adv_upwind;
     float aa[kMaxTaps], ab[kMaxTaps], d[kMaxTaps];
     float dx, dy, dx2, dy2;
+    float rdx, rdy, rdx2, rdy2;   // reciprocals for div_by (correctly rounded quotient without the division sequence)
     long total;
 };
 
@@ -69,8 +71,164 @@ rhs2d_kernel(const RhsParams p) {
     }
 }
 
+// ---- tiled variant: thread = 4 consecutive columns, marching down the rows of a tile ----
+// u1, v1, ax and out rows are 16-byte aligned when W % 4 == 0, so they move as float4; the
+// x-direction window is a rolling set of K float4 in registers (every ax row is loaded once per
+// tile).  The rows of ay have pitch W + 2*halo and start on arbitrary 4-byte phases: they are
+// staged by `cp.async.bulk` (one copy per row, from the enclosing 16-byte boundary) and read back
+// as four aligned float4 per row, from which the K+3 window values are picked for the row's `lead`.
+#ifndef PPNN_RHS_TR
+#define PPNN_RHS_TR 4
+#endif
+constexpr int kRTileCols = 512;
+constexpr int kRPitch = kRTileCols + 16;
+
+template <int K, int LEAD>
+__device__ __forceinline__ void rtile_ywindow(const float* srow, int t, float* yw) {
+    const float4* c = reinterpret_cast<const float4*>(srow) + t;
+    const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    const float v[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+    for (int k = 0; k < K + 3; ++k) yw[k] = v[LEAD + k];
+}
+
+template <int K, int TR>
+__global__ void __launch_bounds__(128)
+rhs2d_tile_kernel(const RhsParams p, const float* ay_end) {
+    // every operand of the tile is staged by TMA: [ax: TR+K-1 rows][u1: TR][v1: TR] x 512 (aligned rows),
+    // [ay: TR rows x kRPitch] (arbitrary 4-byte phase per row -> lead)
+    extern __shared__ __align__(16) float smem_rhs[];
+    float* sax = smem_rhs;
+    float* su = sax + (TR + K - 1) * kRTileCols;
+    float* sv = su + TR * kRTileCols;
+    float* say = sv + TR * kRTileCols;
+    __shared__ __align__(8) uint64_t bar;
+    const int t = threadIdx.x;
+    const int j0 = blockIdx.x * kRTileCols;
+    const int i0 = blockIdx.y * TR;
+    const long b = blockIdx.z;
+    const int rows = min(TR, p.H - i0);
+    const int Wy = p.W + 2 * p.halo;
+    const int wy = min(kRTileCols + K - 1, Wy - j0);            // ay floats per row of this tile
+    const int wx = min(kRTileCols, p.W - j0);                   // multiple of 4
+    const float* ay = p.ay + ((size_t)b * p.H + i0) * Wy + j0;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        const uintptr_t end_al = reinterpret_cast<uintptr_t>(ay_end) & ~(uintptr_t)15;
+        uint32_t total = (uint32_t)((rows + K - 1) + 2 * rows) * wx * 4, nb[TR]; uintptr_t a0[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+            nb[r] = 0;
+            if (r >= rows) continue;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(ay + (size_t)r * Wy);
+            a0[r] = a & ~(uintptr_t)15;
+            nb[r] = (uint32_t)((a - a0[r]) + (size_t)wy * 4 + 15) & ~15u;
+            if (a0[r] + nb[r] > end_al) {                        // last bytes of the tensor: stay inside it
+                float* dst = say + r * kRPitch;
+                for (const float* q = reinterpret_cast<const float*>(end_al); q < ay_end; ++q)
+                    dst[(reinterpret_cast<uintptr_t>(q) - a0[r]) >> 2] = *q;
+                nb[r] = (uint32_t)(end_al - a0[r]);
+            }
+            total += nb[r];
+        }
+        mbar_expect_tx(&bar, total);
+        const float* gx = p.ax + ((size_t)b * (p.H + 2 * p.halo) + i0) * p.W + j0;
+        for (int r = 0; r < rows + K - 1; ++r) bulk_g2s(sax + r * kRTileCols, gx + (size_t)r * p.W, (uint32_t)wx * 4, &bar);
+        const size_t o0 = ((size_t)b * p.H + i0) * p.W + j0;
+        for (int r = 0; r < rows; ++r) {
+            bulk_g2s(su + r * kRTileCols, p.u1 + o0 + (size_t)r * p.W, (uint32_t)wx * 4, &bar);
+            bulk_g2s(sv + r * kRTileCols, p.v1 + o0 + (size_t)r * p.W, (uint32_t)wx * 4, &bar);
+        }
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+            if (nb[r]) bulk_g2s(say + r * kRPitch, reinterpret_cast<const void*>(a0[r]), nb[r], &bar);
+    }
+    __syncthreads();
+    const int jg = j0 + 4 * t;
+    const float mu = __ldg(p.mu + b);
+    mbar_wait(&bar, 0);
+    if (jg >= p.W) return;                                      // W % 4 == 0: a quad is all in or all out
+    const float4* xs = reinterpret_cast<const float4*>(sax) + t;
+    float xw[K][4];
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+        const float4 q = xs[k * (kRTileCols / 4)];
+        xw[k + 1][0] = q.x; xw[k + 1][1] = q.y; xw[k + 1][2] = q.z; xw[k + 1][3] = q.w;
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+        if (r >= rows) break;
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k) { xw[k][0] = xw[k + 1][0]; xw[k][1] = xw[k + 1][1]; xw[k][2] = xw[k + 1][2]; xw[k][3] = xw[k + 1][3]; }
+        {
+            const float4 q = xs[(r + K - 1) * (kRTileCols / 4)];
+            xw[K - 1][0] = q.x; xw[K - 1][1] = q.y; xw[K - 1][2] = q.z; xw[K - 1][3] = q.w;
+        }
+        const float4 u4 = reinterpret_cast<const float4*>(su + r * kRTileCols)[t];
+        const float4 v4 = reinterpret_cast<const float4*>(sv + r * kRTileCols)[t];
+        const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        float yw[K + 3];
+        const float* srow = say + r * kRPitch;
+        const int lead = (int)(reinterpret_cast<uintptr_t>(ay + (size_t)r * Wy) & 15) >> 2;      // warp-uniform
+        switch (lead) {
+        case 0: rtile_ywindow<K, 0>(srow, t, yw); break;
+        case 1: rtile_ywindow<K, 1>(srow, t, yw); break;
+        case 2: rtile_ywindow<K, 2>(srow, t, yw); break;
+        default: rtile_ywindow<K, 3>(srow, t, yw); break;
+        }
+        float res[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float u1 = uu[c], v1 = vv[c];
+            float acc = 0.f;
+            if (p.rhs_id & PPNN_RHS_ADV) {
+                float fx = 0.f, fy = 0.f;
+                if (p.adv_upwind) {
+                    // Upwind1: the forward filter is zero left of the centre, the backward one right of
+                    // it (operators.py:211-218) -- the zero taps add nothing and are skipped
+                    constexpr int C = (K - 1) / 2;
+                    float bx = 0.f, by = 0.f;
+#pragma unroll
+                    for (int k = C; k < K; ++k) { fx += p.aa[k] * xw[k][c]; fy += p.aa[k] * yw[c + k]; }
+#pragma unroll
+                    for (int k = 0; k <= C; ++k) { bx += p.ab[k] * xw[k][c]; by += p.ab[k] * yw[c + k]; }
+                    const float c1 = xw[C][c], c2 = yw[c + C];
+                    fx = c1 <= 0.f ? fx : (c1 > 0.f ? bx : 0.f);
+                    fy = c2 <= 0.f ? fy : (c2 > 0.f ? by : 0.f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { fx += p.aa[k] * xw[k][c]; fy += p.aa[k] * yw[c + k]; }
+                }
+                acc = div_by(-u1 * fx, p.dx, p.rdx) - div_by(v1 * fy, p.dy, p.rdy);
+            }
+            if (p.rhs_id & PPNN_RHS_DIFF) {
+                float lx = 0.f, ly = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { lx += p.d[k] * xw[k][c]; ly += p.d[k] * yw[c + k]; }
+                const float lap = mu * (div_by(lx, p.dx2, p.rdx2) + div_by(ly, p.dy2, p.rdy2));
+                acc = (p.rhs_id & PPNN_RHS_ADV) ? acc + lap : lap;
+            }
+            res[c] = add_reaction(acc, p.rhs_id & ~3, u1, v1);
+        }
+        const size_t o = ((size_t)b * p.H + i0 + r) * p.W + jg;
+        asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + o), "f"(res[0]), "f"(res[1]), "f"(res[2]), "f"(res[3]) : "memory");
+    }
+}
+
 template <int K>
 static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (K > 1 && p.W % 4 == 0 && al(p.u1) && al(p.v1) && al(p.ax) && al(p.out) &&
+        p.H <= 65535) {
+        constexpr int TR = PPNN_RHS_TR;
+        const size_t smem = ((size_t)(TR + K - 1 + 2 * TR) * kRTileCols + (size_t)TR * kRPitch) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(rhs2d_tile_kernel<K, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        dim3 grid((p.W + kRTileCols - 1) / kRTileCols, (p.H + TR - 1) / TR, (unsigned)B);
+        rhs2d_tile_kernel<K, TR><<<grid, 128, smem, s>>>(p, p.ay + (size_t)B * p.H * (p.W + 2 * p.halo));
+        return launch_status();
+    }
     dim3 grid((p.W + 127) / 128, (p.H + kRhsRows - 1) / kRhsRows, (unsigned)B);
     rhs2d_kernel<K><<<grid, 128, 0, s>>>(p);
     return launch_status();
@@ -107,6 +265,7 @@ extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
     p.u1 = u1; p.v1 = v1; p.mu = mu; p.ax = ax; p.ay = ay; p.out = out;
     p.H = H; p.W = W; p.halo = halo; p.rhs_id = rhs_id; p.adv_upwind = adv_scheme == PPNN_UPWIND1;
     p.dx = dx; p.dy = dy; p.dx2 = dx2; p.dy2 = dy2;
+    p.rdx = 1.f / dx; p.rdy = 1.f / dy; p.rdx2 = 1.f / dx2; p.rdy2 = 1.f / dy2;
     p.total = (long)B * H * W;
     if (B > 65535 || (H + kRhsRows - 1) / kRhsRows > 65535) return PPNN_E_SHAPE;
     cudaStream_t s = (cudaStream_t)stream;

@@ -7,6 +7,7 @@
 // owns one column and a run of ROWS outputs so every input row is loaded once
 // per run; along W a thread computes VEC consecutive outputs from K+VEC-1 loads.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ppnn {
 
@@ -54,6 +55,59 @@ stencil_x_kernel(const StencilParams p) {
         if (i0 + q < p.Hout) st_stream(out + (size_t)(i0 + q) * p.Wout, apply_taps<K, UPWIND>(p, w + q));
 }
 
+// ---- along H, staged: (rows + K - 1) x 512 input tile by TMA, 4 columns per thread ----
+// Same idea as the W-direction kernel below: no global load instructions, the whole tile is
+// in flight at once; a thread marches down its 4 columns with a rolling window of K float4
+// read by LDS.128 and stores float4.  Rows are 16-byte aligned here (width % 4 == 0).
+constexpr int kXTileIn = 22;                        // input rows per tile: 22 - K + 1 output rows
+constexpr int kXTileCols = 512;
+
+template <int K, bool UPWIND>
+__global__ void __launch_bounds__(128)
+stencil_x_tma_kernel(const StencilParams p) {
+    constexpr int TR = kXTileIn - K + 1;
+    __shared__ __align__(16) float tile[kXTileIn * kXTileCols];
+    __shared__ __align__(8) uint64_t bar;
+    const int t = threadIdx.x;
+    const int j0 = blockIdx.x * kXTileCols;
+    const int i0 = blockIdx.y * TR;
+    const int rows = min(TR, p.Hout - i0);
+    const int wseg = min(kXTileCols, p.Win - j0);               // multiple of 4
+    const float* in = p.in + ((size_t)blockIdx.z * p.Hin + i0) * p.Win + j0;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bar, (uint32_t)(rows + K - 1) * wseg * 4);
+        for (int r = 0; r < rows + K - 1; ++r)
+            bulk_g2s(tile + r * kXTileCols, in + (size_t)r * p.Win, (uint32_t)wseg * 4, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const int jg = j0 + 4 * t;
+    if (jg >= p.Win) return;
+    const float4* sp = reinterpret_cast<const float4*>(tile) + t;
+    float* out = p.out + ((size_t)blockIdx.z * p.Hout + i0) * p.Wout + jg;
+    float w[4][K];
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+        const float4 q = sp[k * (kXTileCols / 4)];
+        w[0][k + 1] = q.x; w[1][k + 1] = q.y; w[2][k + 1] = q.z; w[3][k + 1] = q.w;
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+        if (r >= rows) break;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < K - 1; ++k) w[c][k] = w[c][k + 1];
+        const float4 q = sp[(r + K - 1) * (kXTileCols / 4)];
+        w[0][K - 1] = q.x; w[1][K - 1] = q.y; w[2][K - 1] = q.z; w[3][K - 1] = q.w;
+        const float o0 = apply_taps<K, UPWIND>(p, w[0]), o1 = apply_taps<K, UPWIND>(p, w[1]),
+                    o2 = apply_taps<K, UPWIND>(p, w[2]), o3 = apply_taps<K, UPWIND>(p, w[3]);
+        asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (size_t)r * p.Wout), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
+    }
+}
+
 // ---- along W (axis 3): grid (col groups, row runs, planes) ---------------------
 template <int K, bool UPWIND>
 __global__ void __launch_bounds__(128)
@@ -71,6 +125,94 @@ stencil_y_kernel(const StencilParams p) {
 #pragma unroll
         for (int q = 0; q < kVec; ++q)
             if (jg + q < p.Wout) st_stream(out + q, apply_taps<K, UPWIND>(p, w + q));
+    }
+}
+
+// ---- along W, staged: TMA row segments -> shared memory -> 4 outputs per thread ----
+// A 'valid' stencil along W reads K consecutive floats per output from rows whose pitch
+// (Wout + K - 1) is not a multiple of 16 bytes, so neither vector loads nor a K-fold reuse in
+// registers come for free.  Here one thread issues a `cp.async.bulk` per row of the tile (from the
+// enclosing 16-byte boundary; `lead` = 0..3 floats to skip, per row), the CTA waits on one
+// mbarrier, and every thread reads FOUR aligned float4 per row and picks its K+3 window values out
+// of those 16 registers (the four `lead` cases are separate, fully unrolled code paths), computes
+// 4 consecutive outputs and stores them as one float4.  LSU work per output: 1 LDS.128 + 1/4
+// STG.128, no global load instructions at all.
+constexpr int kYTileRows = 8;
+constexpr int kYTileCols = 512;                     // outputs per row of a tile: 4 per thread, 128 threads
+constexpr int kYPitch = kYTileCols + 16;            // floats; chunk loads reach 4*t + 15
+
+template <int K, bool UPWIND, int LEAD>
+__device__ __forceinline__ void ytile_row(const StencilParams& p, const float* srow, float* orow, int t, int jg) {
+    const float4* c = reinterpret_cast<const float4*>(srow) + t;
+    const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    const float v[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+    float w[K + 3];
+#pragma unroll
+    for (int k = 0; k < K + 3; ++k) w[k] = v[LEAD + k];
+    float4 o;
+    o.x = apply_taps<K, UPWIND>(p, w);
+    o.y = apply_taps<K, UPWIND>(p, w + 1);
+    o.z = apply_taps<K, UPWIND>(p, w + 2);
+    o.w = apply_taps<K, UPWIND>(p, w + 3);
+    if (jg + 3 < p.Wout) {
+        asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+    } else {
+        if (jg < p.Wout) st_stream(orow, o.x);
+        if (jg + 1 < p.Wout) st_stream(orow + 1, o.y);
+        if (jg + 2 < p.Wout) st_stream(orow + 2, o.z);
+    }
+}
+
+template <int K, bool UPWIND>
+__global__ void __launch_bounds__(128)
+stencil_y_tma_kernel(const StencilParams p, const float* in_end) {
+    __shared__ __align__(16) float tile[kYTileRows * kYPitch];
+    __shared__ __align__(8) uint64_t bar;
+    const int t = threadIdx.x;
+    const int j0 = blockIdx.x * kYTileCols;
+    const int i0 = blockIdx.y * kYTileRows;
+    const int rows = min(kYTileRows, p.Hout - i0);
+    const int wseg = min(kYTileCols + K - 1, p.Win - j0);      // input floats of this tile per row
+    const float* in = p.in + ((size_t)blockIdx.z * p.Hin + i0) * p.Win + j0;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        const uintptr_t end_al = reinterpret_cast<uintptr_t>(in_end) & ~(uintptr_t)15;
+        uint32_t total = 0, nb[kYTileRows]; uintptr_t a0[kYTileRows];
+#pragma unroll
+        for (int r = 0; r < kYTileRows; ++r) {
+            nb[r] = 0;
+            if (r >= rows) continue;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(in + (size_t)r * p.Win);
+            a0[r] = a & ~(uintptr_t)15;
+            nb[r] = (uint32_t)((a - a0[r]) + (size_t)wseg * 4 + 15) & ~15u;
+            if (a0[r] + nb[r] > end_al) {                        // last bytes of the tensor: stay inside it
+                float* dst = tile + r * kYPitch;
+                for (const float* q = reinterpret_cast<const float*>(end_al); q < in_end; ++q)
+                    dst[(reinterpret_cast<uintptr_t>(q) - a0[r]) >> 2] = *q;
+                nb[r] = (uint32_t)(end_al - a0[r]);
+            }
+            total += nb[r];
+        }
+        mbar_expect_tx(&bar, total);
+#pragma unroll
+        for (int r = 0; r < kYTileRows; ++r)
+            if (nb[r]) bulk_g2s(tile + r * kYPitch, reinterpret_cast<const void*>(a0[r]), nb[r], &bar);
+    }
+    __syncthreads();                                             // barrier initialised (and the tail floats written)
+    mbar_wait(&bar, 0);
+    const int jg = j0 + 4 * t;
+    if (jg >= p.Wout) return;
+    float* out = p.out + ((size_t)blockIdx.z * p.Hout + i0) * p.Wout + jg;
+    for (int r = 0; r < rows; ++r, out += p.Wout) {
+        const float* srow = tile + r * kYPitch;
+        const int lead = (int)(reinterpret_cast<uintptr_t>(in + (size_t)r * p.Win) & 15) >> 2;   // warp-uniform
+        switch (lead) {
+        case 0: ytile_row<K, UPWIND, 0>(p, srow, out, t, jg); break;
+        case 1: ytile_row<K, UPWIND, 1>(p, srow, out, t, jg); break;
+        case 2: ytile_row<K, UPWIND, 2>(p, srow, out, t, jg); break;
+        default: ytile_row<K, UPWIND, 3>(p, srow, out, t, jg); break;
+        }
     }
 }
 
@@ -112,9 +254,19 @@ stencil_bwd_kernel(const StencilBwdParams p) {
 
 template <int K, bool UPWIND>
 static int launch_fwd(const StencilParams& p, long planes, int axis, cudaStream_t s) {
-    if (axis == 2) {
+    if (axis == 2 && p.Win % 4 == 0 && ((reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0 &&
+        (p.Hout + 7) / 8 <= 65535) {
+        constexpr int TR = kXTileIn - K + 1;
+        dim3 grid((p.Win + kXTileCols - 1) / kXTileCols, (p.Hout + TR - 1) / TR, (unsigned)planes);
+        stencil_x_tma_kernel<K, UPWIND><<<grid, 128, 0, s>>>(p);
+    } else if (axis == 2) {
         dim3 grid((p.Win + 127) / 128, (p.Hout + kRows - 1) / kRows, (unsigned)planes);
         stencil_x_kernel<K, UPWIND><<<grid, 128, 0, s>>>(p);
+    } else if (p.Wout % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && K + 3 + 3 <= 16 &&
+               (p.Hout + kYTileRows - 1) / kYTileRows <= 65535) {
+        // float4 stores need 16-byte aligned output rows; everything else takes the scalar kernel below
+        dim3 grid((p.Wout + kYTileCols - 1) / kYTileCols, (p.Hout + kYTileRows - 1) / kYTileRows, (unsigned)planes);
+        stencil_y_tma_kernel<K, UPWIND><<<grid, 128, 0, s>>>(p, p.in + (size_t)planes * p.Hin * p.Win);
     } else {
         int groups = (p.Wout + kVec - 1) / kVec;
         dim3 grid((groups + 127) / 128, (p.Hout + kRows - 1) / kRows, (unsigned)planes);

@@ -756,3 +756,52 @@ def test_coarse_step_other_meshes(pk, fine, coarse, rhs):
     a, pn = step.step_inputs(u.cuda(), mu.cuda(), om.cuda(), osd.cuda(), om.cuda(), osd.cuda() * 1e-2)[:2]
     assert_parity(a.cpu(), (u[:, :, :-1, :-1] - om) / osd, TOL, "u_norm")
     assert_parity(pn.cpu(), (ref.detach()[:, :, :-1, :-1] - om) / (osd * 1e-2), TOL, "pdeu_norm")
+
+
+# ------------------------------------------------- Tier A tiled kernels (TMA-staged rows, float4 I/O)
+@pytest.mark.parametrize("b,h,w", [(3, 13, 48), (2, 9, 516), (1, 40, 1024), (2, 3, 2052), (4, 32, 32)])
+def test_tiled_y_stencils_and_fused_rhs(pk, b, h, w):
+    """Widths that are multiples of 4 take the tiled kernels (stencil_y_tma_kernel, rhs2d_tile_kernel):
+    several tiles per row, ragged row tiles, every 16-byte phase of the padded rows."""
+    gen = torch.Generator().manual_seed(100 * h + w)
+    ops, rhs = pk["ops"], pk["rhs"]
+    u1 = torch.randn(b, 1, h, w, generator=gen) * 0.7
+    v1 = torch.randn(b, 1, h, w, generator=gen) * 0.7
+    mu = torch.linspace(0.02, 0.3, b).reshape(-1, 1, 1, 1)
+    for aa, da in ((1, 2), (3, 6), (2, 4)):
+        if 2 * aa + 1 != da + 1:
+            continue
+        o = O.Ops(aa, da)
+        dudx, dudy = ops.dudx_2D(accuracy=aa), ops.dudy_2D(accuracy=aa)
+        d2x, d2y = ops.d2udx2_2D(accuracy=da), ops.d2udy2_2D(accuracy=da)
+        ax, ay = O.wrap_x(u1, aa), O.wrap_y(u1, aa)
+        assert_parity(dudy(ay.cuda()).cpu(), O.upwind2d(ay, aa, 3), TOL, f"dudy acc {aa}")
+        assert_parity(d2y(ay.cuda()).cpu(), O.stencil2d(ay, "Central2", da, 3), TOL, f"d2udy2 acc {da}")
+        for name in ("burgers2DFu", "rdFv", "convecu", "burgers2Dpv"):
+            fld = v1 if name.endswith("v") else u1
+            fx, fy = O.wrap_x(fld, aa), O.wrap_y(fld, aa)
+            ref = O.rhs(name, u1, v1, mu, o, fx, fy, 0.1, 0.08, 0.01, 0.0064)
+            ours = getattr(rhs, name)(u1.cuda(), v1.cuda(), mu.cuda(), dudx, dudy, d2x, d2y, fx.cuda(), fy.cuda(),
+                                      0.1, 0.08, 0.01, 0.0064)
+            assert_parity(ours.cpu(), ref, TOL, f"{name} {aa}/{da} {b}x{h}x{w}")
+
+
+def test_tiled_kernels_at_the_end_of_an_allocation(pk):
+    """The staged copies start at the enclosing 16-byte boundary and are clamped at the end of the
+    tensor: inputs that end exactly at the end of their allocation, NaN guard bands around them."""
+    import ctypes as C
+    L = pk["lib"]
+    lib = L.load()
+    gen = torch.Generator().manual_seed(5)
+    b, h, w, hl = 2, 5, 36, 3
+    wy = w + 2 * hl
+    for off in (0, 1, 2, 3):
+        n = b * h * wy
+        buf = torch.full((off + n,), float("nan"), device="cuda")          # tensor = the tail of the allocation
+        ay = torch.randn(b, 1, h, wy, generator=gen)
+        buf[off:] = ay.reshape(-1).cuda()
+        view = buf[off:].view(b, 1, h, wy)
+        out = torch.empty(b, 1, h, w, device="cuda")
+        L.check(lib.ppnn_stencil_fwd(view.data_ptr(), out.data_ptr(), b, h, wy, 3, 1, 6, L.stream()), "stencil")   # axis 3, Central2, accuracy 6
+        assert_parity(out.cpu(), O.stencil2d(ay, "Central2", 6, 3), TOL, f"offset {off}")
+        assert torch.isfinite(out).all()

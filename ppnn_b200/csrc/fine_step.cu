@@ -311,8 +311,17 @@ static int launch_fine_tma(const FineParams& p, int B, void* stream, bool* used)
     return launch_status();
 }
 
+}  // namespace ppnn
+#include "fine_step_tile.cuh"
+namespace ppnn {
+
 template <int HL, int MODE>
 static int launch_fine(const FineParams& p, int B, void* stream) {
+    {
+        bool used = false;
+        int st = launch_fine_tile<HL, MODE>(p, B, stream, &used);     // wide true-periodic meshes
+        if (used || st != PPNN_OK) return st;
+    }
     {
         bool used = false;
         int st;

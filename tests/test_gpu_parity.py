@@ -325,7 +325,8 @@ def test_fine_solver_against_reference_golden(pk, mode):
 
 @pytest.mark.parametrize("n,endpoint,aa,da", [(257, True, 3, 6), (256, False, 3, 6), (100, True, 1, 2),
                                                (131, False, 2, 4), (1025, True, 3, 6), (1024, False, 3, 6),
-                                               (513, True, 2, 4), (640, False, 1, 2)])
+                                               (513, True, 2, 4), (640, False, 1, 2),
+                                               (2048, False, 3, 6), (3072, False, 1, 2), (2176, False, 2, 4)])
 def test_fine_solver_sizes_and_accuracies(pk, n, endpoint, aa, da):
     gen = torch.Generator().manual_seed(31)
     b = 2

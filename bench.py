@@ -208,7 +208,7 @@ def workload_config(B, n, sample_of=None):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from ppnn_b200 import CoarseStep, FineBurgers, _lib as L
+    from ppnn_b200 import CoarseStep, FineBurgers, HostStepPipeline, _lib as L
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -264,33 +264,16 @@ def run_ours(args):
     ms = timed(kernel_step, args.steps, max(args.warmup, 3))
     value = world * pts / (ms * 1e-3) / 1e9
 
-    # ---- e2e: host buffers, H2D + kernel + D2H per step, chunked over two streams -----
+    # ---- e2e: pinned host buffers -> HostStepPipeline (H2D / kernel / D2H on three streams) ----
     nchunk = 8
-    cb = (B + nchunk - 1) // nchunk
     u_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True).copy_(u)
     nn_h = torch.empty(nn.shape, dtype=torch.float32, pin_memory=True).copy_(nn)
     out_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True)
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    dbuf = [(torch.empty((cb,) + tuple(u.shape[1:]), device=dev), torch.empty((cb,) + tuple(nn.shape[1:]), device=dev),
-             torch.empty((cb,) + tuple(u.shape[1:]), device=dev)) for _ in streams]
+    pipe = HostStepPipeline(step, B, chunks=nchunk, depth=3, device=dev)
+    dbuf = pipe.bufs
 
     def e2e_step():
-        cur = torch.cuda.current_stream()
-        for s in streams:
-            s.wait_stream(cur)
-        for c in range(nchunk):
-            b0, b1 = c * cb, min((c + 1) * cb, B)
-            if b0 >= b1:
-                break
-            s = streams[c % 2]
-            du, dn, do = dbuf[c % 2]
-            with torch.cuda.stream(s):
-                du[:b1 - b0].copy_(u_h[b0:b1], non_blocking=True)
-                dn[:b1 - b0].copy_(nn_h[b0:b1], non_blocking=True)
-                step.step_update_(du[:b1 - b0], muv[b0:b1], dn[:b1 - b0], om, os_, do[:b1 - b0])
-                out_h[b0:b1].copy_(do[:b1 - b0], non_blocking=True)
-        for s in streams:
-            cur.wait_stream(s)
+        pipe.run(u_h, muv, nn_h, om, os_, out_h)
 
     e2e_steps = max(2, min(args.steps, 10))
     ms_e2e = timed(e2e_step, e2e_steps, 1)
@@ -404,8 +387,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e, "steps": e2e_steps, "matches_resident_result": e2e_ok,
-                    "api": "ppnn_b200.CoarseStep.step_update_ -> ppnn_step_update (C ABI), pinned host buffers, "
-                           "8 chunks over 2 streams"},
+                    "api": "ppnn_b200.HostStepPipeline.run -> CoarseStep.step_update_ -> ppnn_step_update (C ABI), pinned "
+                           "host buffers, 8 chunks through separate H2D / kernel / D2H streams (ring of 3 device buffer sets)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "coarse_step_staged_kernel<MODE_UPDATE, 257, HAS_NN>",

@@ -284,6 +284,67 @@ class CoarseStep:
             return result
 
 
+class HostStepPipeline:
+    """``u_next = padBC_rd(nn*outstd+outmean) + u + pde_du(u, mu)`` for states that live in
+    (pinned) HOST memory -- where the reference keeps them between steps (train2D.py:230-245
+    moves every batch ``.to(device)`` and back).
+
+    The batch is cut into chunks that flow through three streams -- H2D copies, the fused kernel,
+    D2H copies -- with a ring of device buffers and events between the stages, so the two copy
+    engines and the SMs all stay busy; the step is PCIe-bound (12 bytes per point-update cross the
+    link: 8 in, 4 out)."""
+
+    def __init__(self, step: "CoarseStep", batch: int, chunks: int = 8, depth: int = 3, device="cuda"):
+        self.step = step
+        self.B = int(batch)
+        self.cb = (self.B + chunks - 1) // chunks
+        self.nchunk = (self.B + self.cb - 1) // self.cb
+        dev = torch.device(device)
+        F = (2, step.FH, step.FW)
+        P = (2, step.FH - 1, step.FW - 1)
+        self.depth = max(2, min(depth, self.nchunk))
+        self.bufs = [(torch.empty((self.cb,) + F, device=dev), torch.empty((self.cb,) + P, device=dev),
+                      torch.empty((self.cb,) + F, device=dev)) for _ in range(self.depth)]
+        self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(self.nchunk)]
+        self.ev_k = [torch.cuda.Event() for _ in range(self.nchunk)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.nchunk)]
+
+    def run(self, u_host: torch.Tensor, mu_dev: torch.Tensor, nn_host: Optional[torch.Tensor],
+            outmean, outstd, out_host: torch.Tensor) -> torch.Tensor:
+        """One step; ``mu_dev`` [B] stays on the device.  Returns ``out_host`` (valid once the
+        current stream has been synchronised)."""
+        cur = torch.cuda.current_stream()
+        for s in (self.s_in, self.s_k, self.s_out):
+            s.wait_stream(cur)
+        om = outmean if isinstance(outmean, C.Array) or outmean is None else L.f2(outmean)
+        osd = outstd if isinstance(outstd, C.Array) or outstd is None else L.f2(outstd)
+        for c in range(self.nchunk):
+            b0, b1 = c * self.cb, min((c + 1) * self.cb, self.B)
+            n = b1 - b0
+            du, dn, do = self.bufs[c % self.depth]
+            with torch.cuda.stream(self.s_in):
+                if c >= self.depth:
+                    self.s_in.wait_event(self.ev_k[c - self.depth])       # the kernel that read this buffer set
+                du[:n].copy_(u_host[b0:b1], non_blocking=True)
+                if nn_host is not None:
+                    dn[:n].copy_(nn_host[b0:b1], non_blocking=True)
+                self.ev_in[c].record(self.s_in)
+            with torch.cuda.stream(self.s_k):
+                self.s_k.wait_event(self.ev_in[c])
+                if c >= self.depth:
+                    self.s_k.wait_event(self.ev_out[c - self.depth])      # its output buffer has been drained
+                self.step.step_update_(du[:n], mu_dev[b0:b1], dn[:n] if nn_host is not None else None, om, osd, do[:n])
+                self.ev_k[c].record(self.s_k)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_k[c])
+                out_host[b0:b1].copy_(do[:n], non_blocking=True)
+                self.ev_out[c].record(self.s_out)
+        for s in (self.s_in, self.s_k, self.s_out):
+            cur.wait_stream(s)
+        return out_host
+
+
 class FineBurgers:
     """Fine-grid explicit Burgers generator (operators.py:403-492).
 

@@ -806,3 +806,27 @@ def test_tiled_kernels_at_the_end_of_an_allocation(pk):
         L.check(lib.ppnn_stencil_fwd(view.data_ptr(), out.data_ptr(), b, h, wy, 3, 1, 6, L.stream()), "stencil")   # axis 3, Central2, accuracy 6
         assert_parity(out.cpu(), O.stencil2d(ay, "Central2", 6, 3), TOL, f"offset {off}")
         assert torch.isfinite(out).all()
+
+
+def test_host_step_pipeline_matches_resident_step(pk):
+    """HostStepPipeline (pinned host buffers, three streams, ring of device buffers) against the same
+    step on resident tensors, ragged last chunk, two consecutive steps reusing the ring."""
+    from ppnn_b200 import HostStepPipeline
+    gen = torch.Generator().manual_seed(3)
+    step = pk["CoarseStep"](65, 13, "rdFu", "rdFv", 0.002, 1.6)
+    B = 23
+    u = torch.randn(B, 2, 65, 65, generator=gen).pin_memory()
+    nn_out = torch.randn(B, 2, 64, 64, generator=gen).pin_memory()
+    mu = torch.linspace(0.2, 1.3, B).cuda()
+    om, osd = [0.01, -0.02], [0.3, 0.2]
+    out = torch.empty_like(u).pin_memory()
+    pipe = HostStepPipeline(step, B, chunks=5, depth=2)
+    for _ in range(2):
+        pipe.run(u, mu, nn_out, om, osd, out)
+        torch.cuda.synchronize()
+        ref = step.step_update(u.cuda(), mu.reshape(-1, 1, 1, 1), nn_out.cuda(), om, osd)
+        assert torch.equal(out, ref.cpu())
+        u.copy_(out)
+    pipe.run(u, mu, None, None, None, out)                      # PDE-only step
+    torch.cuda.synchronize()
+    assert torch.equal(out, step.step_update(u.cuda(), mu.reshape(-1, 1, 1, 1)).cpu())

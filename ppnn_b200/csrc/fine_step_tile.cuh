@@ -3,8 +3,10 @@
 //
 // fine_step_tma_kernel keeps whole rows in its shared-memory ring, which stops fitting at
 // ~1088 columns.  Here the plane is cut into `ntile` column tiles of Wt <= 1024 columns and
-// the unit of work is one row of one (sample, tile); a persistent CTA owns a contiguous range
-// of units.  A ring row holds [4 halo | Wt | 4 halo] floats, so
+// the unit of work is one row of one (sample, tile).  CTAs come in groups of `ntile`: the CTAs of
+// a group walk the SAME contiguous range of (sample, row) pairs, one column tile each, so that at
+// any moment the group streams whole rows (DRAM pages are not visited in 4 KB pieces at a 16-32 KB
+// stride).  A ring row holds [4 halo | Wt | 4 halo] floats, so
 //   * every copy is a 16-byte-aligned `cp.async.bulk` (W, Wt and the tile origins are
 //     multiples of 4 floats): one copy per row for interior tiles, main + wrapped halo
 //     chunks for the first / last tile -- no ordinary loads anywhere in the producer;
@@ -20,8 +22,8 @@ namespace ppnn {
 constexpr int kTileHalo = 4;           // halo floats kept on each side of a ring row (>= HL, 16-byte chunk)
 
 struct FineTilePlan {
-    long total_units;      // B * ntile * H rows
-    long units_per_cta;
+    long total_units;      // B * H (sample, row) pairs
+    long units_per_cta;    // ... per CTA group
     int ntile, Wt;         // column tiles per plane, columns per tile
     int lanes;             // Wt / 2
     int cwarps;
@@ -46,7 +48,8 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == pl.cwarps;
     const size_t plane = (size_t)p.H * W;
-    const long g0 = (long)blockIdx.x * pl.units_per_cta;
+    const int tile = (int)(blockIdx.x % pl.ntile);              // this CTA's column tile
+    const long g0 = (long)(blockIdx.x / pl.ntile) * pl.units_per_cta;
     const long g1 = min(g0 + pl.units_per_cta, pl.total_units);
 
     if (tid == 0) {
@@ -62,9 +65,8 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
         long cidx = 0;
         int pslot = 0; uint32_t pphase = 0;
         for (long g = g0; g < g1;) {
-            const long bt = g / p.H;
+            const int b = (int)(g / p.H);
             const int r0 = (int)(g % p.H);
-            const int b = (int)(bt / pl.ntile), tile = (int)(bt % pl.ntile);
             const int c0 = tile * Wt;
             const int r1 = (int)min((long)p.H, r0 + (g1 - g));
             const int nb = (r1 - r0 + R - 1) / R;
@@ -105,9 +107,8 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
     auto next_slot = [&](int& sl, uint32_t& ph) { if (++sl == pl.ring) { sl = 0; ph ^= 1; } };
 
     for (long g = g0; g < g1;) {
-        const long bt = g / p.H;
+        const int b = (int)(g / p.H);
         const int r0 = (int)(g % p.H);
-        const int b = (int)(bt / pl.ntile), tile = (int)(bt % pl.ntile);
         const int r1 = (int)min((long)p.H, r0 + (g1 - g));
         const int nb = (r1 - r0 + R - 1) / R;
         float* ouA = p.uo + (size_t)b * plane + (size_t)r0 * W + tile * Wt + colA;
@@ -238,7 +239,7 @@ static int launch_fine_tile(const FineParams& p, int B, void* stream, bool* used
     pl.lanes = pl.Wt / 2;
     pl.cwarps = (pl.lanes + 31) / 32;
     pl.band_floats = kTmaRows * (pl.Wt + 2 * kTileHalo);
-    pl.total_units = (long)B * pl.ntile * p.H;
+    pl.total_units = (long)B * p.H;
     void (*kern)(FineParams, FineTilePlan) = pl.Wt == 1024 ? fine_step_tile_kernel<HL, MODE, 1024> : fine_step_tile_kernel<HL, MODE, 0>;
     const size_t band_bytes = (size_t)2 * pl.band_floats * sizeof(float);
     int ring = (int)((200 * 1024) / band_bytes);
@@ -251,11 +252,13 @@ static int launch_fine_tile(const FineParams& p, int B, void* stream, bool* used
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long nctas = sms;
-    long units = (pl.total_units + nctas - 1) / nctas;
+    long ngroups = sms / pl.ntile;                              // one CTA per SM, whole groups only
+    if (ngroups < 1) ngroups = 1;
+    long units = (pl.total_units + ngroups - 1) / ngroups;
     if (units < 4 * kTmaRows) units = 4 * kTmaRows;
-    nctas = (pl.total_units + units - 1) / units;
+    ngroups = (pl.total_units + units - 1) / units;
     pl.units_per_cta = units;
+    const long nctas = ngroups * pl.ntile;
     kern<<<(unsigned)nctas, (pl.cwarps + 1) * 32, smem, (cudaStream_t)stream>>>(p, pl);
     *used = true;
     return launch_status();

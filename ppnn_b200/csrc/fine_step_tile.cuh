@@ -226,23 +226,27 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
 template <int HL, int MODE>
 static int launch_fine_tile(const FineParams& p, int B, void* stream, bool* used) {
     *used = false;
-    if (getenv("PPNN_NO_TMA")) return PPNN_OK;
+    if (getenv("PPNN_NO_TMA") || getenv("PPNN_NO_TILE")) return PPNN_OK;
     // true periodic, 16-byte aligned rows, too wide for whole rows in the ring
-    if (p.PW != p.W || p.PH != p.H || p.W % 4 != 0 || p.W < 1024 || p.H < 2 * kTmaRows) return PPNN_OK;
+    if (p.PW != p.W || p.PH != p.H || p.W % 8 != 0 || p.W < 256 || p.H < 2 * kTmaRows) return PPNN_OK;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.v);
     if (al & 15) return PPNN_OK;
     FineTilePlan pl;
     pl.ntile = (p.W + 1023) / 1024;
     if (p.W % pl.ntile != 0) return PPNN_OK;
     pl.Wt = p.W / pl.ntile;
-    if (pl.Wt % 8 != 0 || pl.Wt < 512) return PPNN_OK;
+    if (pl.Wt % 8 != 0 || pl.Wt < 256) return PPNN_OK;
     pl.lanes = pl.Wt / 2;
     pl.cwarps = (pl.lanes + 31) / 32;
     pl.band_floats = kTmaRows * (pl.Wt + 2 * kTileHalo);
     pl.total_units = (long)B * p.H;
     void (*kern)(FineParams, FineTilePlan) = pl.Wt == 1024 ? fine_step_tile_kernel<HL, MODE, 1024> : fine_step_tile_kernel<HL, MODE, 0>;
+    // narrow tiles: several persistent CTAs per SM (4 consumer warps each at 256 columns), smaller rings
+    int cpsm = 1024 / pl.Wt;
+    if (cpsm < 1) cpsm = 1;
+    if (cpsm > 4) cpsm = 4;
     const size_t band_bytes = (size_t)2 * pl.band_floats * sizeof(float);
-    int ring = (int)((200 * 1024) / band_bytes);
+    int ring = (int)((200 * 1024 / cpsm) / band_bytes);
     if (ring > kTmaMaxRing) ring = kTmaMaxRing;
     if (ring < 4) return PPNN_OK;
     pl.ring = ring;
@@ -252,7 +256,7 @@ static int launch_fine_tile(const FineParams& p, int B, void* stream, bool* used
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long ngroups = sms / pl.ntile;                              // one CTA per SM, whole groups only
+    long ngroups = (long)sms * cpsm / pl.ntile;                 // persistent CTAs, whole groups only
     if (ngroups < 1) ngroups = 1;
     long units = (pl.total_units + ngroups - 1) / ngroups;
     if (units < 4 * kTmaRows) units = 4 * kTmaRows;

@@ -3,9 +3,12 @@
 // f <- f + dt*rhs(f) generators (operators.py:494-748), on periodic grids with
 // or without the duplicated endpoint.
 //
-// Two kernels: the TMA-fed persistent kernel of fine_step_tma.cuh (meshes of ~512 to
-// 1088 columns, e.g. the 1024 / 1025 generator meshes) and the register-window
-// kernel below (every other size).
+// Three kernels, tried in this order (launch_fine):
+//   fine_step_tile.cuh  TMA-fed persistent kernel on column tiles: true-periodic meshes whose
+//                       rows are 16-byte aligned (256 ... 8192 columns, e.g. 1024^2)
+//   fine_step_ep.cuh    TMA-fed persistent kernel for rows on arbitrary 4-byte phases: the
+//                       duplicated-endpoint meshes of the reference (513^2, 1025^2)
+//   below               register-window kernel: every other size (257^2, tiny meshes)
 //
 // Layout: u, v are [B, H, W] fp32, W contiguous.  One CTA = (32k-column chunk,
 // PAIR of row bands, sample).  A thread owns one column and walks down both bands
@@ -269,66 +272,23 @@ fine_step_kernel(const FineParams p) {
 }
 
 }  // namespace ppnn
-#include "fine_step_tma.cuh"
-namespace ppnn {
-
-template <int HL, int MODE, int WC>
-static int launch_fine_tma(const FineParams& p, int B, void* stream, bool* used) {
-    *used = false;
-    if (getenv("PPNN_NO_TMA")) return PPNN_OK;
-    const int lanes = (p.W + 1) / 2;
-    const int cwarps = (lanes + 31) / 32;
-    // narrow meshes leave a CTA with too few consumer warps: the register-window kernel wins there
-    if (cwarps > 17 || cwarps < 8 || p.H < 2 * kTmaRows || ((long)p.PH * p.W) % 4 != 0) return PPNN_OK;
-    FineTmaPlan pl;
-    pl.total_rows = (long)B * p.H;
-    pl.lanes = lanes; pl.cwarps = cwarps;
-    pl.band_floats = (kTmaRows * p.W + 8 + 3) & ~3;
-    pl.u_end = p.u + (size_t)B * p.H * p.W;
-    pl.v_end = p.v + (size_t)B * p.H * p.W;
-    auto kern = fine_step_tma_kernel<HL, MODE, WC>;
-    const size_t band_bytes = (size_t)2 * pl.band_floats * sizeof(float);
-    int ring = (int)((200 * 1024) / band_bytes);
-    if (ring > kTmaMaxRing) ring = kTmaMaxRing;
-    if (ring < 4) return PPNN_OK;
-    pl.ring = ring;
-    const size_t smem = (size_t)ring * band_bytes;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int threads = (cwarps + 1) * 32;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    if (per_sm < 1) return PPNN_OK;
-    long nctas = (long)sms * per_sm;
-    long rows = (pl.total_rows + nctas - 1) / nctas;
-    if (rows < 4 * kTmaRows) rows = 4 * kTmaRows;            // keep the 2-band lead-in per range small
-    nctas = (pl.total_rows + rows - 1) / rows;
-    pl.rows_per_cta = rows;
-    kern<<<(unsigned)nctas, threads, smem, (cudaStream_t)stream>>>(p, pl);
-    *used = true;
-    return launch_status();
-}
-
-}  // namespace ppnn
 #include "fine_step_tile.cuh"
+#include "fine_step_ep.cuh"
 namespace ppnn {
 
 template <int HL, int MODE>
 static int launch_fine(const FineParams& p, int B, void* stream) {
     {
         bool used = false;
-        int st = launch_fine_tile<HL, MODE>(p, B, stream, &used);     // wide true-periodic meshes
+        int st = launch_fine_tile<HL, MODE>(p, B, stream, &used);     // true-periodic meshes with aligned rows
         if (used || st != PPNN_OK) return st;
     }
     {
-        bool used = false;
+        bool used = false;                                            // duplicated endpoint / odd widths up to 1088 columns
         int st;
-        if (HL == 3 && p.W == 1025) st = launch_fine_tma<HL, MODE, 1025>(p, B, stream, &used);
-        else if (HL == 3 && p.W == 257) st = launch_fine_tma<HL, MODE, 257>(p, B, stream, &used);
-        else if (HL == 3 && p.W == 1024) st = launch_fine_tma<HL, MODE, 1024>(p, B, stream, &used);
-        else st = launch_fine_tma<HL, MODE, 0>(p, B, stream, &used);
+        if (HL == 3 && p.W == 1025) st = launch_fine_ep<HL, MODE, 1025>(p, B, stream, &used);
+        else if (HL == 3 && p.W == 257) st = launch_fine_ep<HL, MODE, 257>(p, B, stream, &used);
+        else st = launch_fine_ep<HL, MODE, 0>(p, B, stream, &used);
         if (used || st != PPNN_OK) return st;
     }
     // columns per CTA: whole warps, as few idle lanes as possible, <= 384 threads

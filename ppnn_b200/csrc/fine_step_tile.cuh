@@ -1,8 +1,7 @@
 // Column-tiled TMA variant of the fine-grid solver step for WIDE true-periodic meshes
-// (2048, 4096, 8192 columns; included by fine_step.cu after fine_step_tma.cuh).
+// (256 ... 8192 columns; included by fine_step.cu).
 //
-// fine_step_tma_kernel keeps whole rows in its shared-memory ring, which stops fitting at
-// ~1088 columns.  Here the plane is cut into `ntile` column tiles of Wt <= 1024 columns and
+// Whole rows in the shared-memory ring stop fitting at ~1088 columns.  Here the plane is cut into `ntile` column tiles of Wt <= 1024 columns and
 // the unit of work is one row of one (sample, tile).  CTAs come in groups of `ntile`: the CTAs of
 // a group walk the SAME contiguous range of (sample, row) pairs, one column tile each, so that at
 // any moment the group streams whole rows (DRAM pages are not visited in 4 KB pieces at a 16-32 KB
@@ -12,12 +11,16 @@
 //     chunks for the first / last tile -- no ordinary loads anywhere in the producer;
 //   * the y-direction taps are plain immediates: the periodic column wrap is resolved by
 //     the producer, there are no seam warps.
-// The consumer side is the one of fine_step_tma_kernel: lanes own columns t and t + Wt/2
+// Consumer side: lanes own columns t and t + Wt/2
 // packed in float2 (FFMA2), x-direction taps in a register window fed from the ring.
 #pragma once
-#include "fine_step_tma.cuh"
+#include <type_traits>
+#include "tma.cuh"
 
 namespace ppnn {
+
+constexpr int kTmaRows = 4;            // rows per ring band = rows per compute batch
+constexpr int kTmaMaxRing = 8;
 
 constexpr int kTileHalo = 4;           // halo floats kept on each side of a ring row (>= HL, 16-byte chunk)
 
@@ -30,6 +33,50 @@ struct FineTilePlan {
     int ring;
     int band_floats;       // floats per (slot, field): kTmaRows * (Wt + 8)
 };
+
+// One explicit update of a packed pair of grid points from its x-direction windows (xu, xv: 2*HL+1
+// rows centred on the point) and y-direction windows (yu, yv).
+template <int HL, int MODE>
+__device__ __forceinline__ void fine_point_update(const FineParams& p, float mu, float2 c, float2 vcen,
+                                                  const float2* xu, const float2* xv, const float2* yu, const float2* yv,
+                                                  float2& unew, float2& vnew) {
+    if (MODE == FINE_GENERIC) {
+        float2 ru = f2(0.f), rv = f2(0.f);
+        if (p.rhs_u & PPNN_RHS_ADV)
+            ru = add2(mul2(mul2(neg2(c), upwind2<HL>(p, c, xu)), f2(p.rdx)),
+                      neg2(mul2(mul2(vcen, upwind2<HL>(p, c, yu)), f2(p.rdy))));
+        if (p.rhs_u & PPNN_RHS_DIFF) {
+            float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, xu), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
+            ru = (p.rhs_u & PPNN_RHS_ADV) ? add2(ru, lap) : lap;
+        }
+        ru = react2(ru, p.rhs_u & ~3, c, vcen);
+        if (p.rhs_v & PPNN_RHS_ADV)
+            rv = add2(mul2(mul2(neg2(c), upwind2<HL>(p, vcen, xv)), f2(p.rdx)),
+                      neg2(mul2(mul2(vcen, upwind2<HL>(p, vcen, yv)), f2(p.rdy))));
+        if (p.rhs_v & PPNN_RHS_DIFF) {
+            float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, xv), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
+            rv = (p.rhs_v & PPNN_RHS_ADV) ? add2(rv, lap) : lap;
+        }
+        rv = react2(rv, p.rhs_v & ~3, c, vcen);
+        unew = fma2(p.dt, ru, c);
+        vnew = fma2(p.dt, rv, vcen);
+    } else {
+        // burgers2Dpu then burgers2Dpv with the updated u (operators.py:474-475)
+        const float2 dxu = upwind2<HL>(p, c, xu), dyu = upwind2<HL>(p, c, yu);
+        const float2 lapu = mul2(f2(mu), add2(mul2(central2<HL>(p, xu), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
+        const float2 advy = neg2(mul2(mul2(vcen, dyu), f2(p.rdy)));
+        unew = fma2(p.dt, add2(add2(mul2(mul2(neg2(c), dxu), f2(p.rdx)), advy), lapu), c);
+        if (MODE == FINE_AS_WRITTEN) {
+            // quirk Q3: v is advected and diffused with u's derivative fields
+            vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxu), f2(p.rdx)), advy), lapu), vcen);
+        } else {
+            const float2 dxv = upwind2<HL>(p, vcen, xv), dyv = upwind2<HL>(p, vcen, yv);
+            const float2 lapv = mul2(f2(mu), add2(mul2(central2<HL>(p, xv), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
+            vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxv), f2(p.rdx)),
+                                        neg2(mul2(mul2(vcen, dyv), f2(p.rdy)))), lapv), vcen);
+        }
+    }
+}
 
 template <int HL, int MODE, int WTC>
 __global__ void __launch_bounds__(544)
@@ -166,40 +213,7 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
                 const float2 c = wu[HL + q];
                 const float2 vcen = VWIN ? wv[HL + q] : make_float2(vr[0], vr[dB]);
                 float2 unew, vnew;
-                if (MODE == FINE_GENERIC) {
-                    float2 ru = f2(0.f), rv = f2(0.f);
-                    if (p.rhs_u & PPNN_RHS_ADV)
-                        ru = add2(mul2(mul2(neg2(c), upwind2<HL>(p, c, wu + q)), f2(p.rdx)),
-                                  neg2(mul2(mul2(vcen, upwind2<HL>(p, c, yu)), f2(p.rdy))));
-                    if (p.rhs_u & PPNN_RHS_DIFF) {
-                        float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, wu + q), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
-                        ru = (p.rhs_u & PPNN_RHS_ADV) ? add2(ru, lap) : lap;
-                    }
-                    ru = react2(ru, p.rhs_u & ~3, c, vcen);
-                    if (p.rhs_v & PPNN_RHS_ADV)
-                        rv = add2(mul2(mul2(neg2(c), upwind2<HL>(p, vcen, wv + q)), f2(p.rdx)),
-                                  neg2(mul2(mul2(vcen, upwind2<HL>(p, vcen, yv)), f2(p.rdy))));
-                    if (p.rhs_v & PPNN_RHS_DIFF) {
-                        float2 lap = mul2(f2(mu), add2(mul2(central2<HL>(p, wv + q), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
-                        rv = (p.rhs_v & PPNN_RHS_ADV) ? add2(rv, lap) : lap;
-                    }
-                    rv = react2(rv, p.rhs_v & ~3, c, vcen);
-                    unew = fma2(p.dt, ru, c);
-                    vnew = fma2(p.dt, rv, vcen);
-                } else {
-                    const float2 dxu = upwind2<HL>(p, c, wu + q), dyu = upwind2<HL>(p, c, yu);
-                    const float2 lapu = mul2(f2(mu), add2(mul2(central2<HL>(p, wu + q), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
-                    const float2 advy = neg2(mul2(mul2(vcen, dyu), f2(p.rdy)));
-                    unew = fma2(p.dt, add2(add2(mul2(mul2(neg2(c), dxu), f2(p.rdx)), advy), lapu), c);
-                    if (MODE == FINE_AS_WRITTEN) {
-                        vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxu), f2(p.rdx)), advy), lapu), vcen);
-                    } else {
-                        const float2 dxv = upwind2<HL>(p, vcen, wv + q), dyv = upwind2<HL>(p, vcen, yv);
-                        const float2 lapv = mul2(f2(mu), add2(mul2(central2<HL>(p, wv + q), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
-                        vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxv), f2(p.rdx)),
-                                                    neg2(mul2(mul2(vcen, dyv), f2(p.rdy)))), lapv), vcen);
-                    }
-                }
+                fine_point_update<HL, MODE>(p, mu, c, vcen, wu + q, wv + (VWIN ? q : 0), yu, yv, unew, vnew);
                 if (active && r0 + n * R + q < r1) {
                     ouA[(size_t)q * W] = unew.x; ovA[(size_t)q * W] = vnew.x;
                     ouA[(size_t)q * W + dB] = unew.y; ovA[(size_t)q * W + dB] = vnew.y;

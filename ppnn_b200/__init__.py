@@ -17,7 +17,7 @@ All device work goes through the C ABI of ``libppnn_b200.so`` (include/ppnn_b200
 There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .fused import CoarseStep, FineBurgers, FineRhsSolver, HostStepPipeline  # noqa: F401
+from .fused import CoarseStep, FineBurgers, FineRhsSolver, HostStepPipeline, RolloutPlan  # noqa: F401
 
 __all__ = ["CoarseStep", "FineBurgers", "FineRhsSolver", "operators", "rhs", "utility"]
 from .dataset import PdeDataset  # noqa: F401

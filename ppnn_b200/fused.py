@@ -234,54 +234,78 @@ class CoarseStep:
         [B, nsteps, 2, F, F].  ``stats`` holds inmean/instd/outmean/outstd/mumean/mustd
         (+ pdemean/pdestd).  ``graph=True`` captures one whole step (K1 -> net -> K2)
         in a CUDA graph and replays it, which is what makes B = 6..12 rollouts
-        launch-latency free."""
-        self._check_state(u)
-        x = L.dev(u, "state").clone()
-        B = x.shape[0]
-        muv = _mu_vec(mu, B, x.device)
-        mun = ((muv - stats["mumean"].to(x.device)) / stats["mustd"].to(x.device)).reshape(B, 1, 1, 1)
-        om, os_ = L.f2(stats["outmean"]), L.f2(stats["outstd"])
-        im, is_ = L.f2(stats["inmean"]), L.f2(stats["instd"])
-        pm, ps = (L.f2(stats["pdemean"]), L.f2(stats["pdestd"])) if uses_pde else (None, None)
-        ostd_t, omean_t = stats["outstd"].to(x.device), stats["outmean"].to(x.device)
-        result = torch.empty((B, nsteps) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
-        nxt = torch.empty_like(x)
+        launch-latency free; to reuse the captured graph over many rollouts of the same
+        batch size keep the :class:`RolloutPlan` (``prepare_rollout``)."""
+        return self.prepare_rollout(net, u.shape[0], mu, stats, uses_pde, graph, device=u.device).run(u, nsteps)
 
-        def one_step(src, dst):
-            if uses_pde:
-                un, pn, _ = self.step_inputs(src, muv, im, is_, pm, ps)
-                nn_out = net(un, mun, pn)
-            else:
-                un, _, _ = self.step_inputs(src, muv, im, is_)
-                nn_out = net(un, mun)
-            if uses_pde:
-                self.step_update_(src, muv, nn_out.contiguous(), om, os_, dst)
-            else:       # train2D.py:240-242: no PDE increment at all
-                dst.copy_(torch.nn.functional.pad(nn_out * ostd_t + omean_t, (0, 1, 0, 1), mode="circular") + src)
+    def prepare_rollout(self, net: Callable, batch: int, mu, stats: Dict[str, torch.Tensor],
+                        uses_pde: bool = True, graph: bool = True, device="cuda") -> "RolloutPlan":
+        return RolloutPlan(self, net, batch, mu, stats, uses_pde, graph, device)
 
+
+class RolloutPlan:
+    """One rollout configuration (network, batch size, parameters, statistics) with its static
+    buffers and, with ``graph=True``, the CUDA graph of one step  K1 -> net -> K2 -> state copy.
+    ``run(u0, nsteps)`` only replays; the capture (cuDNN autotune, allocator warm-up, graph
+    instantiation) is paid once in the constructor."""
+
+    def __init__(self, step: CoarseStep, net: Callable, batch: int, mu, stats: Dict[str, torch.Tensor],
+                 uses_pde: bool = True, graph: bool = True, device="cuda"):
+        self.step, self.net, self.uses_pde = step, net, uses_pde
+        dev = torch.device(device)
+        B = int(batch)
+        self.x = torch.zeros(B, 2, step.FH, step.FW, dtype=torch.float32, device=dev)
+        self.nxt = torch.empty_like(self.x)
+        self.muv = _mu_vec(mu, B, dev)
+        self.mun = ((self.muv - stats["mumean"].to(dev)) / stats["mustd"].to(dev)).reshape(B, 1, 1, 1)
+        self.om, self.os_ = L.f2(stats["outmean"]), L.f2(stats["outstd"])
+        self.im, self.is_ = L.f2(stats["inmean"]), L.f2(stats["instd"])
+        self.pm, self.ps = (L.f2(stats["pdemean"]), L.f2(stats["pdestd"])) if uses_pde else (None, None)
+        self.ostd_t, self.omean_t = stats["outstd"].to(dev), stats["outmean"].to(dev)
+        self.graph = None
+        if graph:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.Stream()
+                stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(stream):
+                    for _ in range(2):                      # warm-up outside capture (cudnn autotune, allocs)
+                        self._one_step(self.x, self.nxt)
+                torch.cuda.current_stream().wait_stream(stream)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._one_step(self.x, self.nxt)
+                    self.x.copy_(self.nxt)
+                self.graph = g
+
+    def _one_step(self, src, dst):
+        st = self.step
+        if self.uses_pde:
+            un, pn, _ = st.step_inputs(src, self.muv, self.im, self.is_, self.pm, self.ps)
+            nn_out = self.net(un, self.mun, pn)
+            st.step_update_(src, self.muv, nn_out.contiguous(), self.om, self.os_, dst)
+        else:       # train2D.py:240-242: no PDE increment at all
+            un, _, _ = st.step_inputs(src, self.muv, self.im, self.is_)
+            nn_out = self.net(un, self.mun)
+            dst.copy_(torch.nn.functional.pad(nn_out * self.ostd_t + self.omean_t, (0, 1, 0, 1), mode="circular") + src)
+
+    def run(self, u: torch.Tensor, nsteps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B,2,F,F] -> [B, nsteps, 2, F, F] (``out`` may be a preallocated result tensor)."""
+        self.step._check_state(u)
+        x = self.x
+        result = out if out is not None else torch.empty((x.shape[0], nsteps) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            if not graph:
+            x.copy_(L.dev(u, "state"))
+            if self.graph is not None:
                 for t in range(nsteps):
-                    one_step(x, nxt)
+                    self.graph.replay()
+                    result[:, t] = x
+            else:
+                nxt = self.nxt
+                for t in range(nsteps):
+                    self._one_step(x, nxt)
                     x, nxt = nxt, x
                     result[:, t] = x
-                return result
-            # graph: a static state buffer is advanced in place
-            stream = torch.cuda.Stream()
-            stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(stream):
-                for _ in range(2):                      # warm-up outside capture (cudnn autotune, allocs)
-                    one_step(x, nxt)
-            torch.cuda.current_stream().wait_stream(stream)
-            x.copy_(L.dev(u, "state"))
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                one_step(x, nxt)
-                x.copy_(nxt)
-            for t in range(nsteps):
-                g.replay()
-                result[:, t] = x
-            return result
+        return result
 
 
 class HostStepPipeline:

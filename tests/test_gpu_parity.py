@@ -830,3 +830,23 @@ def test_host_step_pipeline_matches_resident_step(pk):
     pipe.run(u, mu, None, None, None, out)                      # PDE-only step
     torch.cuda.synchronize()
     assert torch.equal(out, step.step_update(u.cuda(), mu.reshape(-1, 1, 1, 1)).cpu())
+
+
+@pytest.mark.parametrize("n,b", [(2048, 3), (1024, 5), (512, 7)])
+def test_fine_step_translation_equivariance_at_full_size(pk, n, b):
+    """Size-independent property at meshes the oracle cannot afford: on a true periodic grid one step
+    commutes with a cyclic shift of the fields, bit for bit (every point runs the same arithmetic wherever
+    it sits: tile edges, CTA row ranges, ring wrap-around, producer-resolved periodic halos)."""
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    u = torch.rand(b, n, n, device="cuda", generator=gen) - 0.4
+    v = torch.rand(b, n, n, device="cuda", generator=gen) - 0.5
+    mu = torch.linspace(0.025, 0.065, b, device="cuda")
+    for mode in ("as_written", "intended"):
+        fb = pk["FineBurgers"](mode=mode, endpoint=False)
+        u1, v1 = fb.step(u, v, mu)
+        for sh in ((37, 1000 % n), (n - 1, 3)):
+            us, vs = torch.roll(u, sh, dims=(1, 2)).contiguous(), torch.roll(v, sh, dims=(1, 2)).contiguous()
+            u2, v2 = fb.step(us, vs, mu)
+            assert torch.equal(u2, torch.roll(u1, sh, dims=(1, 2))), f"{mode} u shift {sh}"
+            assert torch.equal(v2, torch.roll(v1, sh, dims=(1, 2))), f"{mode} v shift {sh}"
+        assert torch.isfinite(u1).all() and torch.isfinite(v1).all()

@@ -96,6 +96,13 @@ int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
  * F.interpolate(mode='bilinear'|'bicubic', size=(Hout,Wout), align_corners).    */
 int ppnn_resample_fwd(const float* in, float* out, long planes, int Hin, int Win,
                       int Hout, int Wout, int mode, int align_corners, void* stream);
+
+/* The same on input planes that are `in_plane_stride` floats apart (each plane itself dense,
+ * row-major): lets the caller pass a channel slice such as u[:, :1] of a [B,2,H,W] state, which is
+ * what train2D.py:68-69 hands to mesh_convertor.down, without a contiguous copy. */
+int ppnn_resample_fwd_strided(const float* in, float* out, long planes, long in_plane_stride,
+                              int Hin, int Win, int Hout, int Wout, int mode, int align_corners,
+                              void* stream);
 /* adjoint w.r.t. `in`; grad_in [planes,Hin,Win] is zero-filled then accumulated. */
 int ppnn_resample_bwd(const float* grad_out, float* grad_in, long planes, int Hin, int Win,
                       int Hout, int Wout, int mode, int align_corners, void* stream);

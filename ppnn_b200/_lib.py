@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ppnn_stencil_bwd": (C.c_int, [_P, _P, _P, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ppnn_rhs2d_fwd": (C.c_int, [_P] * 6 + [C.c_int] * 9 + [C.c_float] * 4 + [_P]),
     "ppnn_resample_fwd": (C.c_int, [_P, _P, C.c_long] + [C.c_int] * 6 + [_P]),
+    "ppnn_resample_fwd_strided": (C.c_int, [_P, _P, C.c_long, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_resample_bwd": (C.c_int, [_P, _P, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_pde_du_fwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_int, _P]),
     "ppnn_pde_du_bwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

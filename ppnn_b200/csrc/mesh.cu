@@ -12,6 +12,7 @@ namespace ppnn {
 struct ResampleParams {
     const float* in; float* out;
     int Hin, Win, Hout, Wout;
+    long in_stride;  // floats between consecutive input planes (Hin*Win when dense; forward only)
     int align;
     float sh, sw;
     long total;     // planes * Hout * Wout
@@ -26,7 +27,7 @@ resample_kernel(const ResampleParams p) {
         long t = idx / p.Wout;
         int i = (int)(t % p.Hout);
         long pl = t / p.Hout;
-        size_t base = (size_t)pl * p.Hin * p.Win;
+        size_t base = BWD ? (size_t)pl * p.Hin * p.Win : (size_t)pl * p.in_stride;
         float g = BWD ? __ldg(p.in + idx) : 0.f;        // BWD: `in` is grad_out, `out` is grad_in
         if (MODE == PPNN_BILINEAR) {
             float si = resample_src(p.sh, i, p.align, false), sj = resample_src(p.sw, j, p.align, false);
@@ -107,7 +108,7 @@ bicubic_up_kernel(const ResampleParams p) {
     cubic_weights(sj - fj, wj);
     const int c0 = clampi(j0 - 1, 0, p.Win - 1), c1 = clampi(j0, 0, p.Win - 1),
               c2 = clampi(j0 + 1, 0, p.Win - 1), c3 = clampi(j0 + 2, 0, p.Win - 1);
-    const float* in = p.in + (size_t)blockIdx.z * p.Hin * p.Win;
+    const float* in = p.in + (size_t)blockIdx.z * p.in_stride;
     float* out = p.out + ((size_t)blockIdx.z * p.Hout + r0) * p.Wout + j;
     auto wpass = [&](int I) -> float {
         const float* q = in + (size_t)clampi(I, 0, p.Hin - 1) * p.Win;
@@ -127,14 +128,14 @@ bicubic_up_kernel(const ResampleParams p) {
     }
 }
 
-static int run_resample(const float* in, float* out, long planes, int Hin, int Win, int Hout, int Wout,
+static int run_resample(const float* in, float* out, long planes, long in_stride, int Hin, int Win, int Hout, int Wout,
                         int mode, int align, bool bwd, void* stream) {
     if (!in || !out) return PPNN_E_NULL;
-    if (planes < 0 || Hin < 1 || Win < 1 || Hout < 1 || Wout < 1) return PPNN_E_SHAPE;
+    if (planes < 0 || Hin < 1 || Win < 1 || Hout < 1 || Wout < 1 || in_stride < (long)Hin * Win) return PPNN_E_SHAPE;
     if (mode != PPNN_BILINEAR && mode != PPNN_BICUBIC) return PPNN_E_MODE;
     if (planes == 0) return PPNN_OK;
     ResampleParams p;
-    p.in = in; p.out = out; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout;
+    p.in = in; p.out = out; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.in_stride = in_stride;
     p.align = align != 0;
     p.sh = resample_scale(Hin, Hout, p.align);
     p.sw = resample_scale(Win, Wout, p.align);
@@ -168,12 +169,17 @@ using namespace ppnn;
 
 extern "C" int ppnn_resample_fwd(const float* in, float* out, long planes, int Hin, int Win,
                                  int Hout, int Wout, int mode, int align_corners, void* stream) {
-    return run_resample(in, out, planes, Hin, Win, Hout, Wout, mode, align_corners, false, stream);
+    return run_resample(in, out, planes, (long)Hin * Win, Hin, Win, Hout, Wout, mode, align_corners, false, stream);
+}
+
+extern "C" int ppnn_resample_fwd_strided(const float* in, float* out, long planes, long in_plane_stride, int Hin, int Win,
+                                         int Hout, int Wout, int mode, int align_corners, void* stream) {
+    return run_resample(in, out, planes, in_plane_stride, Hin, Win, Hout, Wout, mode, align_corners, false, stream);
 }
 
 extern "C" int ppnn_resample_bwd(const float* grad_out, float* grad_in, long planes, int Hin, int Win,
                                  int Hout, int Wout, int mode, int align_corners, void* stream) {
-    return run_resample(grad_out, grad_in, planes, Hin, Win, Hout, Wout, mode, align_corners, true, stream);
+    return run_resample(grad_out, grad_in, planes, (long)Hin * Win, Hin, Win, Hout, Wout, mode, align_corners, true, stream);
 }
 
 extern "C" int ppnn_abi_version(void) { return PPNN_B200_ABI_VERSION; }

@@ -30,15 +30,31 @@ def _hw(size: Size) -> Tuple[int, int]:
     return int(size), int(size)
 
 
+def _plane_stride(x):
+    """Stride (in elements) between the planes of a [B, 1, H, W] channel slice whose planes are dense --
+    e.g. ``u[:, :1]`` of a contiguous [B, 2, H, W] state (train2D.py:68-69) -- else None."""
+    if (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
+            and not x.is_contiguous() and x.stride(3) == 1 and x.stride(2) == x.shape[3]
+            and x.stride(0) >= x.shape[2] * x.shape[3]):
+        return x.stride(0)
+    return None
+
+
 def _resample_forward(x, hout, wout, mode, align):
     lib = L.load()
-    x = L.dev(x, "mesh_convertor input")
+    stride = _plane_stride(x)
+    if stride is None:
+        x = L.dev(x, "mesh_convertor input")
     hin, win = x.shape[-2], x.shape[-1]
     planes = x.numel() // (hin * win)
     out = torch.empty(x.shape[:-2] + (hout, wout), dtype=torch.float32, device=x.device)
     with L.on_device(x):
-        L.check(lib.ppnn_resample_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, hout, wout,
-                                      mode, int(align), L.stream()), "ppnn_resample_fwd")
+        if stride is None:
+            L.check(lib.ppnn_resample_fwd(x.data_ptr(), out.data_ptr(), planes, hin, win, hout, wout,
+                                          mode, int(align), L.stream()), "ppnn_resample_fwd")
+        else:                       # channel slice: read in place, no contiguous copy
+            L.check(lib.ppnn_resample_fwd_strided(x.data_ptr(), out.data_ptr(), planes, stride, hin, win, hout, wout,
+                                                  mode, int(align), L.stream()), "ppnn_resample_fwd_strided")
     return out, (planes, hin, win, hout, wout, mode, int(align), x.shape)
 
 

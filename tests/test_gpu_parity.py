@@ -850,3 +850,25 @@ def test_fine_step_translation_equivariance_at_full_size(pk, n, b):
             assert torch.equal(u2, torch.roll(u1, sh, dims=(1, 2))), f"{mode} u shift {sh}"
             assert torch.equal(v2, torch.roll(v1, sh, dims=(1, 2))), f"{mode} v shift {sh}"
         assert torch.isfinite(u1).all() and torch.isfinite(v1).all()
+
+
+def test_mesh_converter_on_channel_slices(pk):
+    """train2D.py:68-69 calls ``down(u[:, :1])`` / ``down(u[:, 1:])``: the strided entry point reads the
+    slice in place and must give exactly what the dense one gives on a contiguous copy, with gradients."""
+    gen = torch.Generator().manual_seed(9)
+    M = pk["mesh"]
+    u = torch.randn(5, 2, 65, 65, generator=gen).cuda()
+    m = M(65, 13, dim=2)
+    for c in (0, 1):
+        sl = u[:, c:c + 1]
+        assert not sl.is_contiguous()
+        assert torch.equal(m.down(sl), m.down(sl.contiguous()))
+        assert torch.equal(m.up(sl[:, :, :13, :13]), m.up(sl[:, :, :13, :13].contiguous()))      # rows not dense: copy path
+    ur = u.clone().requires_grad_(True)
+    y = m.down(ur[:, 1:])
+    cot = torch.randn(y.shape, generator=gen).cuda()
+    (g1,) = torch.autograd.grad(y, ur, cot)
+    uc = u.clone().requires_grad_(True)
+    (g2,) = torch.autograd.grad(torch.nn.functional.interpolate(uc[:, 1:], size=13, mode="bilinear", align_corners=True), uc, cot)
+    assert_parity(g1.cpu(), g2.cpu(), TOL, "grad through a sliced down")
+    assert g1[:, 0].abs().max() == 0

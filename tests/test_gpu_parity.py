@@ -872,3 +872,16 @@ def test_mesh_converter_on_channel_slices(pk):
     (g2,) = torch.autograd.grad(torch.nn.functional.interpolate(uc[:, 1:], size=13, mode="bilinear", align_corners=True), uc, cot)
     assert_parity(g1.cpu(), g2.cpu(), TOL, "grad through a sliced down")
     assert g1[:, 0].abs().max() == 0
+
+
+def test_end_to_end_example_runs(pk):
+    """examples/train_one_step.py: generator -> PdeDataset -> one-step training -> captured rollout, tiny sizes."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_one_step", os.path.join(root, "examples", "train_one_step.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses, err = mod.main(["--mesh", "65", "--coarse", "9", "--para", "2", "--repeat", "1", "--gen-steps", "601",
+                            "--epochs", "2", "--batch", "2"])
+    assert len(losses) == 2 and all(math.isfinite(x) for x in losses) and math.isfinite(err)

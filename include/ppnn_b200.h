@@ -130,6 +130,14 @@ int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                     const float* grad_out, float* grad_u, float* grad_mu,
                     int B, int add_identity, void* stream);
 
+/* Backward of ppnn_step_update in one launch: grad_u = grad_out + J^T grad_out (as ppnn_pde_du_bwd with
+ * add_identity), grad_mu [B] (may be NULL) and grad_nn [B,2,FH-1,FW-1] (may be NULL) = outstd * padBC_rd^T(grad_out),
+ * the gradient of the network output (train2D.py:235-238).  grad_nn needs the reference mesh family (last fine
+ * column on the last coarse node, FW-1 a multiple of 32); otherwise PPNN_E_SHAPE: compose it from grad_out. */
+int ppnn_step_update_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                         const float* grad_out, const float* outstd,
+                         float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream);
+
 /* Network inputs of one rollout step (src/train2D.py:235-237), fused with pde_du:
  *   u_norm    [B,2,FH-1,FW-1] = (u[:,:,:-1,:-1]      - inmean ) / instd
  *   pdeu_norm [B,2,FH-1,FW-1] = (pde_du(u)[:,:,:-1,:-1] - pdemean) / pdestd

@@ -28,6 +28,8 @@ constexpr int kMaxSupport = 96;     // fine columns that can touch one coarse co
 struct AdjParams {
     const float* u; const float* mu; const float* g;
     float* gu; float* gmu;
+    float* gnn;        // grad of the network output [B,2,FH-1,FW-1] (padBC_rd^T of grad_out, times outstd) or null
+    float os[2];       // outstd per channel
     int add_identity;
     int apitch;        // pitch of A rows (odd => conflict-free column walks)
     int support;       // table width (<= kMaxSupport)
@@ -269,9 +271,9 @@ coarse_adjoint_kernel(const CoarseParams p, const AdjParams a) {
 
 using namespace ppnn;
 
-extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
-                               const float* grad_out, float* grad_u, float* grad_mu,
-                               int B, int add_identity, void* stream) {
+static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                       const float* grad_out, float* grad_u, float* grad_mu, float* grad_nn, const float* outstd,
+                       int B, int add_identity, void* stream) {
     if (!u || !mu || !grad_out || !grad_u) return PPNN_E_NULL;
     CoarseParams p;
     int st = fill_coarse_params(cfg, &p);
@@ -280,12 +282,16 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
     if (B == 0) return PPNN_OK;
     AdjParams a;
     a.u = u; a.mu = mu; a.g = grad_out; a.gu = grad_u; a.gmu = grad_mu; a.add_identity = add_identity;
+    a.gnn = grad_nn; a.os[0] = outstd ? outstd[0] : 1.f; a.os[1] = outstd ? outstd[1] : 1.f;
     a.apitch = p.FW | 1;
     // fine columns whose 4-tap window can reach one coarse column: 4 / suw (+ slack)
     int support = (int)(4.0f / p.suw) + 4;
     if (support > kMaxSupport) return PPNN_E_TOOBIG;
     if (support > p.FW) support = p.FW;
     a.support = support;
+    // the fused network-output gradient needs the last fine column on the last coarse node (see the kernel)
+    const float slast = p.suw * (float)(p.FW - 1);
+    const bool gnn_ok = (p.FW - 1) % 32 == 0 && floorf(slast) == slast && (int)slast >= p.CW - 1;
     // staged path: (sample, field) CTAs in 2-CTA clusters, TMA ring (coarse_adjoint_staged.cuh)
     {
         AdjStagedLayout lay;
@@ -305,7 +311,7 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
         size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3) * sizeof(int) +
                        ((size_t)((p.CW * support + 3) & ~3) + ((nn2 + 3) & ~3) + (((size_t)(p.CH + 4) * lay.apitch + 3) & ~(size_t)3) + un) * sizeof(float);
         if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 112 * 1024 &&
-            grad_u != grad_out && !getenv("PPNN_NO_TMA")) {
+            grad_u != grad_out && !getenv("PPNN_NO_TMA") && (!grad_nn || gnn_ok)) {
             void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
             if (p.FW == 257) kern = add_identity ? coarse_adjoint_staged_kernel<257, true> : coarse_adjoint_staged_kernel<257, false>;
             else             kern = add_identity ? coarse_adjoint_staged_kernel<0, true> : coarse_adjoint_staged_kernel<0, false>;
@@ -320,6 +326,7 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
             return launch_status();
         }
     }
+    if (grad_nn) return PPNN_E_SHAPE;          // only the staged kernel fuses the network-output gradient
     size_t smem = (size_t)4 * p.NH * p.NW * sizeof(float) + (size_t)p.FH * (sizeof(float4) + sizeof(int)) +
                   (size_t)p.CW * sizeof(int) + (size_t)p.CW * support * sizeof(float) +
                   (size_t)2 * p.CH * a.apitch * sizeof(float);
@@ -332,4 +339,17 @@ extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const
     if (warps < 4) warps = 4;
     coarse_adjoint_kernel<<<B, warps * 32, smem, (cudaStream_t)stream>>>(p, a);
     return launch_status();
+}
+
+extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                               const float* grad_out, float* grad_u, float* grad_mu,
+                               int B, int add_identity, void* stream) {
+    return run_adjoint(cfg, u, mu, grad_out, grad_u, grad_mu, nullptr, nullptr, B, add_identity, stream);
+}
+
+extern "C" int ppnn_step_update_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                                    const float* grad_out, const float* outstd,
+                                    float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream) {
+    if (grad_nn && !outstd) return PPNN_E_NULL;
+    return run_adjoint(cfg, u, mu, grad_out, grad_u, grad_mu, grad_nn, outstd, B, 1, stream);
 }

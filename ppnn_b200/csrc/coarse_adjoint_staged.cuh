@@ -205,7 +205,15 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             if (active) Af[rr * lay.apitch] += v;
         };
         const bool dupl = coldup && j == 0;
-        auto row_in = [&](int qq, int advbits, const float* sg) {
+        const bool GNN = a.gnn != nullptr && coldup;             // (the launcher only passes gnn for such meshes)
+        const float os_f = f ? a.os[1] : a.os[0];
+        float* np = GNN ? a.gnn + ((size_t)b * 2 + f) * (size_t)(p.FH - 1) * (FW - 1) + (size_t)rs * (FW - 1) + jc : nullptr;
+        float gtop = 0.f;                                        // grad_out(FH-1, jc) (+ the corner for column 0): folds onto row 0
+        if (GNN && g == 0 && active) {
+            gtop = ld_stream(gf + (size_t)(p.FH - 1) * FW + jc);
+            if (dupl) gtop += ld_stream(gf + (size_t)(p.FH - 1) * FW + FW - 1);
+        }
+        auto row_in = [&](int qq, int row, int advbits, const float* sg) {
             if ((advbits >> qq) & 1) {                           // retire the oldest slot (warp-uniform)
                 flush(base - 1, c0);
                 c0 = c1; c1 = c2; c2 = c3; c3 = 0.f;
@@ -217,6 +225,12 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
                 const float ge = sg[qq * FW + FW - 1];
                 st_stream(op + (size_t)qq * FW + FW - 1, IDENT ? ge : 0.f);
                 gv += ge;
+            }
+            if (GNN) {
+                // transpose of padBC_rd on the network output: column FW-1 folds onto column 0 (gv already holds
+                // it for the lane of column 0), row FH-1 onto row 0 (gtop), times outstd
+                if (active && jc < FW - 1 && row < p.FH - 1)
+                    st_stream(np + (size_t)qq * (FW - 1), (row == 0 ? gv + gtop : gv) * os_f);
             }
             const float4 wx = wrow[qq];
             c0 += wx.x * gv; c1 += wx.y * gv; c2 += wx.z * gv; c3 += wx.w * gv;
@@ -232,20 +246,21 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             if (++s == kAdjStages) { s = 0; ph ^= 1u; sg = sg_base; } else { sg += gstep; }
             wrow += R;
             op += (size_t)R * FW;
+            if (GNN) np += (size_t)R * (FW - 1);
         };
         int t = 0;
         for (; t < nfull; ++t) {
             const int advbits = advp[t];
             mbar_wait_addr(full_a + 8u * s, ph);
 #pragma unroll
-            for (int qq = 0; qq < R; ++qq) row_in(qq, advbits, sg);
+            for (int qq = 0; qq < R; ++qq) row_in(qq, rs + t * R + qq, advbits, sg);
             advance();
         }
         for (; t < lay.nsteps; ++t) {                            // ragged last band; steps only the other group has
             const int r0 = rs + t * R;
             const int advbits = advp[t];
             mbar_wait_addr(full_a + 8u * s, ph);
-            for (int qq = 0; r0 + qq < re; ++qq) row_in(qq, advbits, sg);
+            for (int qq = 0; r0 + qq < re; ++qq) row_in(qq, r0 + qq, advbits, sg);
             advance();
         }
         flush(base - 1, c0); flush(base, c1); flush(base + 1, c2); flush(base + 2, c3);

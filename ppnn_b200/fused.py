@@ -102,22 +102,31 @@ class _StepUpdateFn(torch.autograd.Function):
         g = L.dev(g, "step_update grad")
         B = x.shape[0]
         gu = gmu = gnn = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        want_nn = ctx.has_nn and ctx.needs_input_grad[2]
+        want_mu = ctx.mu_shape is not None and ctx.needs_input_grad[1]
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or want_nn:
             gu = torch.empty_like(x)
-            want_mu = ctx.mu_shape is not None and ctx.needs_input_grad[1]
             gmu = torch.empty(B, dtype=torch.float32, device=x.device) if want_mu else None
+            st = ctx.step
+            gnn = torch.empty(B, 2, st.FH - 1, st.FW - 1, dtype=torch.float32, device=x.device) if want_nn else None
             with torch.cuda.device(x.device):
-                L.check(lib.ppnn_pde_du_bwd(C.byref(ctx.step.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
-                                            gu.data_ptr(), L.ptr(gmu), B, 1, L.stream()), "ppnn_pde_du_bwd")
+                # one launch: grad_u, grad_mu and the gradient of the network output
+                status = lib.ppnn_step_update_bwd(C.byref(st.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
+                                                  (C.c_float * 2)(*ctx.outstd) if want_nn else None,
+                                                  gu.data_ptr(), L.ptr(gmu), L.ptr(gnn), B, L.stream())
+                if status == L.E_SHAPE and want_nn:
+                    # meshes outside the reference family: adjoint kernel + padBC_rd^T composed on the device
+                    L.check(lib.ppnn_pde_du_bwd(C.byref(st.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
+                                                gu.data_ptr(), L.ptr(gmu), B, 1, L.stream()), "ppnn_pde_du_bwd")
+                    gnn = g[:, :, :-1, :-1].clone()
+                    gnn[:, :, 0, :] += g[:, :, -1, :-1]
+                    gnn[:, :, :, 0] += g[:, :, :-1, -1]
+                    gnn[:, :, 0, 0] += g[:, :, -1, -1]
+                    gnn = gnn * torch.tensor(ctx.outstd, device=g.device).reshape(1, 2, 1, 1)
+                else:
+                    L.check(status, "ppnn_step_update_bwd")
             if want_mu:
                 gmu = gmu.sum().reshape(ctx.mu_shape) if ctx.mu_shape.numel() == 1 and B != 1 else gmu.reshape(ctx.mu_shape)
-        if ctx.has_nn and ctx.needs_input_grad[2]:
-            # transpose of padBC_rd: the appended row / column fold back onto row / column 0
-            gnn = g[:, :, :-1, :-1].clone()
-            gnn[:, :, 0, :] += g[:, :, -1, :-1]
-            gnn[:, :, :, 0] += g[:, :, :-1, -1]
-            gnn[:, :, 0, 0] += g[:, :, -1, -1]
-            gnn = gnn * torch.tensor(ctx.outstd, device=g.device).reshape(1, 2, 1, 1)
         return gu, gmu, gnn, None, None, None
 
 

@@ -754,6 +754,14 @@ def test_coarse_step_other_meshes(pk, fine, coarse, rhs):
         assert_parity(gm.cpu(), gm_ref, 5e-5, "grad_mu")
     upd = step.step_update(u.cuda(), mu.cuda(), nn_out.cuda(), om.cuda(), osd.cuda())
     assert_parity(upd.cpu(), O.ppnn_update(u, ref.detach(), nn_out, om, osd), TOL, "update")
+    # backward of the update: grad_u, grad_mu and the network-output gradient (fused where the mesh allows it)
+    ur2, nr2 = u.clone().requires_grad_(True), nn_out.clone().requires_grad_(True)
+    ref_upd = O.ppnn_update(ur2, ref_pde_du(ur2, mu), nr2, om, osd)
+    gu_r, gn_r = torch.autograd.grad(ref_upd, (ur2, nr2), cot)
+    uc2, nc2 = u.cuda().requires_grad_(True), nn_out.cuda().requires_grad_(True)
+    gu_o, gn_o = torch.autograd.grad(step.step_update(uc2, mu.cuda(), nc2, om.cuda(), osd.cuda()), (uc2, nc2), cot.cuda())
+    assert_parity(gu_o.cpu(), gu_r, TOL, "update grad_u")
+    assert_parity(gn_o.cpu(), gn_r, TOL, "update grad_nn")
     a, pn = step.step_inputs(u.cuda(), mu.cuda(), om.cuda(), osd.cuda(), om.cuda(), osd.cuda() * 1e-2)[:2]
     assert_parity(a.cpu(), (u[:, :, :-1, :-1] - om) / osd, TOL, "u_norm")
     assert_parity(pn.cpu(), (ref.detach()[:, :, :-1, :-1] - om) / (osd * 1e-2), TOL, "pdeu_norm")

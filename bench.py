@@ -303,6 +303,15 @@ def run_ours(args):
                                         gmu.data_ptr(), B, 1, L.stream()), "bwd")
         t = timed(adj, reps, 2)
         extras["step_adjoint"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
+        # backward of the whole update in one launch: grad_u, grad_mu and the network-output gradient
+        gnn = torch.empty_like(nn)
+
+        def upd_bwd():
+            L.check(lib.ppnn_step_update_bwd(C.byref(step.cfg), u.data_ptr(), muv.data_ptr(), out.data_ptr(), os_,
+                                             gu.data_ptr(), gmu.data_ptr(), gnn.data_ptr(), B, L.stream()), "update bwd")
+        t = timed(upd_bwd, reps, 2)
+        extras["step_update_bwd"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 12, "hbm_gbs": 12 * pts / t / 1e6}
+        del gnn
         # training-set precompute (train2D.py:109-151): statistics pass and emit pass over (u, u_next) pairs
         part = torch.empty(B, 2, 6, dtype=torch.float64, device=dev)
         t = timed(lambda: L.check(lib.ppnn_dataset_stats(C.byref(step.cfg), u.data_ptr(), out.data_ptr(), muv.data_ptr(),

@@ -313,8 +313,12 @@ static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* 
         if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 112 * 1024 &&
             grad_u != grad_out && !getenv("PPNN_NO_TMA") && (!grad_nn || gnn_ok)) {
             void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
-            if (p.FW == 257) kern = add_identity ? coarse_adjoint_staged_kernel<257, true> : coarse_adjoint_staged_kernel<257, false>;
-            else             kern = add_identity ? coarse_adjoint_staged_kernel<0, true> : coarse_adjoint_staged_kernel<0, false>;
+            // (the network-output gradient only exists for the update, i.e. with the identity term)
+            if (grad_nn && !add_identity) return PPNN_E_SHAPE;
+            if (p.FW == 257) kern = grad_nn ? coarse_adjoint_staged_kernel<257, true, true>
+                                  : add_identity ? coarse_adjoint_staged_kernel<257, true, false> : coarse_adjoint_staged_kernel<257, false, false>;
+            else             kern = grad_nn ? coarse_adjoint_staged_kernel<0, true, true>
+                                  : add_identity ? coarse_adjoint_staged_kernel<0, true, false> : coarse_adjoint_staged_kernel<0, false, false>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
             const float* g_end = grad_out + (size_t)B * 2 * p.FH * p.FW;

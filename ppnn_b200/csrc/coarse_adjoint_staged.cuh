@@ -43,7 +43,7 @@ struct AdjStagedLayout {
     int nchunk, wmain;
 };
 
-template <int FWC, bool IDENT>
+template <int FWC, bool IDENT, bool WITH_GNN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAdjThreads, 2)
 coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjStagedLayout lay,
                              const float* g_end) {
@@ -205,7 +205,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             if (active) Af[rr * lay.apitch] += v;
         };
         const bool dupl = coldup && j == 0;
-        const bool GNN = a.gnn != nullptr && coldup;             // (the launcher only passes gnn for such meshes)
+        const bool GNN = WITH_GNN && coldup;                     // (the launcher only passes gnn for such meshes)
         const float os_f = f ? a.os[1] : a.os[0];
         float* np = GNN ? a.gnn + ((size_t)b * 2 + f) * (size_t)(p.FH - 1) * (FW - 1) + (size_t)rs * (FW - 1) + jc : nullptr;
         float gtop = 0.f;                                        // grad_out(FH-1, jc) (+ the corner for column 0): folds onto row 0
@@ -246,7 +246,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
             if (++s == kAdjStages) { s = 0; ph ^= 1u; sg = sg_base; } else { sg += gstep; }
             wrow += R;
             op += (size_t)R * FW;
-            if (GNN) np += (size_t)R * (FW - 1);
+            if (WITH_GNN) np += (size_t)R * (FW - 1);
         };
         int t = 0;
         for (; t < nfull; ++t) {

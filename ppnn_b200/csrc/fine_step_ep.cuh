@@ -178,6 +178,12 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
     int slot = 0; uint32_t phase = 0;
     auto next_slot = [&](int& sl, uint32_t& ph) { if (++sl == pl.ring) { sl = 0; ph ^= 1; } };
 
+    // Odd widths (W = 2^k + 1) leave the last consumer warp with ONE live column.  Walking the rows with a
+    // register window like the others would cost a full warp's instruction stream for it (1/17 of the issue
+    // slots at 1025, 1/9 at 513); instead lane q of that warp takes row q of the band and reads all its taps
+    // from the three resident bands, i.e. one pass per band instead of one per row.
+    const bool lonely = (pl.lanes & 31) == 1 && warp == pl.cwarps - 1;
+
     for (long g = g0; g < g1;) {
         const int b = (int)(g / p.H);
         const int r0 = (int)(g % p.H);
@@ -186,6 +192,55 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
         float* ouA = p.uo + (size_t)b * plane + (size_t)r0 * W + colA;
         float* ovA = p.vo + (size_t)b * plane + (size_t)r0 * W + colA;
         const float mu = __ldg(p.mu + b);
+
+        if (lonely) {
+            const int col = pl.lanes - 1;                          // == colA of lane 0
+            float* ou = p.uo + (size_t)b * plane + (size_t)r0 * W + col;
+            float* ov = p.vo + (size_t)b * plane + (size_t)r0 * W + col;
+            int sp = slot; uint32_t php = phase;                   // bands n-1, n, n+1
+            int sc = sp; uint32_t phc = php; next_slot(sc, phc);
+            int sn = sc; uint32_t phn = phc; next_slot(sn, phn);
+            mbar_wait(&ready[sp], php);
+            mbar_wait(&ready[sc], phc);
+            for (int n = 0; n < nb; ++n) {
+                mbar_wait(&ready[sn], phn);
+                if (lane < R) {
+                    const int q = lane;
+                    float2 xu[2 * HL + 1], xv[VWIN ? 2 * HL + 1 : 1], yu[2 * HL + 1], yv[VWIN ? 2 * HL + 1 : 1];
+#pragma unroll
+                    for (int k = 0; k <= 2 * HL; ++k) {
+                        const int rr = q + k - HL;
+                        const int sl = rr < 0 ? sp : rr < R ? sc : sn;
+                        const int row = rr < 0 ? rr + R : rr < R ? rr : rr - R;
+                        const float* fb = ringbuf + (size_t)sl * slot_floats + row * SW + FRONT + col;
+                        xu[k] = make_float2(fb[leads[sl][0][row]], 0.f);
+                        if (VWIN) xv[k] = make_float2(fb[band_floats + leads[sl][1][row]], 0.f);
+                    }
+                    const float* ur = ringbuf + (size_t)sc * slot_floats + q * SW + FRONT + col + leads[sc][0][q];
+                    const float* vr = ringbuf + (size_t)sc * slot_floats + band_floats + q * SW + FRONT + col + leads[sc][1][q];
+#pragma unroll
+                    for (int k = 0; k <= 2 * HL; ++k) {
+                        yu[k] = make_float2(ur[k - HL], 0.f);
+                        if (VWIN) yv[k] = make_float2(vr[k - HL], 0.f);
+                    }
+                    const float2 c = xu[HL];
+                    const float2 vcen = make_float2(vr[0], 0.f);
+                    float2 unew, vnew;
+                    fine_point_update<HL, MODE>(p, mu, c, vcen, xu, xv, yu, yv, unew, vnew);
+                    if (r0 + n * R + q < r1) { ou[(size_t)q * W] = unew.x; ov[(size_t)q * W] = vnew.x; }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[sp]);
+                sp = sc; php = phc; sc = sn; phc = phn;
+                next_slot(sn, phn);
+                ou += (size_t)R * W; ov += (size_t)R * W;
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&empty[sp]); mbar_arrive(&empty[sc]); }
+            slot = sn; phase = phn;
+            g += r1 - r0;
+            continue;
+        }
 
         int s0 = slot; uint32_t ph0 = phase;
         int s1 = s0; uint32_t ph1 = ph0; next_slot(s1, ph1);

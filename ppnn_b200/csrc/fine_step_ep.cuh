@@ -327,9 +327,10 @@ template <int HL, int MODE, int WC>
 static int launch_fine_ep(const FineParams& p, int B, void* stream, bool* used) {
     *used = false;
     if (getenv("PPNN_NO_TMA") || getenv("PPNN_NO_EP")) return PPNN_OK;
-    // rows that the aligned tile kernel does not take; whole rows must fit a ring row
-    // (narrower meshes leave a CTA with too few consumer warps: the register-window kernel wins there)
-    if (p.W < 449 || p.W > 1088 || p.H < 2 * kTmaRows) return PPNN_OK;
+    // rows that the aligned tile kernel does not take; whole rows must fit a ring row.  From the reference's
+    // own 257^2 up (4 CTAs of 4 + 1 consumer warps per SM) this kernel beats the register-window one
+    // (257^2: 0.134 -> 0.124 ms at B = 512, intended mode 0.227 -> 0.174 ms); narrower meshes stay there.
+    if (p.W < 257 || p.W > 1088 || p.H < 2 * kTmaRows) return PPNN_OK;
     if ((reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.v)) & 15) return PPNN_OK;   // first row: lead 0, nothing in front of it
     FineEpPlan pl;
     pl.lanes = (p.W + 1) / 2;
@@ -340,11 +341,13 @@ static int launch_fine_ep(const FineParams& p, int B, void* stream, bool* used) 
     pl.u_end = p.u + (size_t)B * p.H * p.W;
     pl.v_end = p.v + (size_t)B * p.H * p.W;
     auto kern = fine_step_ep_kernel<HL, MODE, WC>;
-    int cpsm = 1024 / p.W;
+    // persistent CTAs per SM: two up to 544 columns (513^2: 9 + 1 warps and a 5-band ring each; one CTA of 9
+    // consumer warps left the SM at 65 % of the copy bandwidth, two reach 81 %)
+    int cpsm = 1088 / p.W;
     if (cpsm < 1) cpsm = 1;
     if (cpsm > 4) cpsm = 4;
     const size_t band_bytes = (size_t)2 * pl.band_floats * sizeof(float);
-    int ring = (int)((200 * 1024 / cpsm) / band_bytes);
+    int ring = (int)(((cpsm > 1 ? 180 : 200) * 1024 / cpsm) / band_bytes);
     if (ring > kTmaMaxRing) ring = kTmaMaxRing;
     if (ring < 4) return PPNN_OK;
     pl.ring = ring;

@@ -124,7 +124,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     __syncthreads();
     if (!producer) {
         for (int idx = tid; idx < p.CW * lay.support; idx += kAdjWarps * 32) {
-            int J = idx / lay.support, k = idx - J * lay.support;
+            int J = small_div(idx, lay.support), k = idx - J * lay.support;
             int j = jstart[J] + k;
             float wsum = 0.f;
             if (j < FW) {
@@ -269,7 +269,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     if (ngroups == 2) {           // fold row group 1's overlap rows back
         const int ovl_lo = max(rowi[lay.split] - 1, 0);
         for (int idx = tid; idx < 4 * lay.apitch; idx += kAdjThreads) {
-            const int k = idx / lay.apitch, j = idx - k * lay.apitch;
+            const int k = small_div(idx, lay.apitch), j = idx - k * lay.apitch;
             if (ovl_lo + k < p.CH) A[(ovl_lo + k) * lay.apitch + j] += A[(p.CH + k) * lay.apitch + j];
         }
         __syncthreads();
@@ -280,7 +280,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     const bool both = ((rid_own | rid_oth) & PPNN_RHS_ADV) || ((rid_own | rid_oth) & ~3);
     const int nthr = kAdjThreads;
     for (int idx = tid; idx < nn2; idx += nthr) {
-        int Jp = idx / p.NH, Ip = idx - Jp * p.NH;                // lanes vary in I: A pitch is odd
+        int Jp = small_div(idx, p.NH), Ip = idx - Jp * p.NH;                // lanes vary in I: A pitch is odd
         float sum = 0.f;
         for (int ej = 0; ej < 2; ++ej) {
             if (ej && Jp != 0) break;
@@ -311,7 +311,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     float part = 0.f;
     if (a.gmu && (rid_own & PPNN_RHS_DIFF))
         for (int idx = tid; idx < nn2; idx += nthr) {
-            int I = idx / p.NW, J = idx - I * p.NW;
+            int I = small_div(idx, p.NW), J = idx - I * p.NW;
             part += (central_x(p, own, I, J) / p.dx2 + central_y(p, own, I, J) / p.dy2) * q[idx];
         }
 #pragma unroll
@@ -342,7 +342,7 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
 
     // ---- phase 3 + 4: own field's coarse cotangent, scatter through D_down^T ------
     for (int idx = tid; idx < nn2; idx += nthr) {
-        int I = idx / p.NW, J = idx - I * p.NW;
+        int I = small_div(idx, p.NW), J = idx - I * p.NW;
         const float q_own = q[idx];
         float cot = stencil_adjoint(p, rid_own, own, cu, cv, q, I, J, mu);
         float q_o = 0.f;

@@ -9,6 +9,13 @@
 
 namespace ppnn {
 
+// idx / n for 0 <= idx < 2^21 and 1 <= n without the ~20-instruction integer-division sequence: (idx + 0.5) / n is
+// at least 0.5 / n away from an integer and the fp32 product is off by less than idx / n * 2^-22.
+__device__ __forceinline__ int small_div(int idx, int n) {
+    return __float2int_rz(((float)idx + 0.5f) * (1.0f / (float)n));
+}
+
+
 // Kernel-parameter block (lives in the constant bank; taps are read from there).
 struct CoarseParams {
     int FH, FW;          // fine points incl. duplicated endpoint
@@ -212,14 +219,14 @@ __device__ __forceinline__ void coarse_rhs_phase(const CoarseParams& p, const fl
     const int nn2 = p.NH * p.NW;
     if (p.adv_n == 2 && p.diff_n == 3) {
         for (int idx = tid; idx < nn2; idx += nthr) {
-            int I = idx / p.NW, J = idx - I * p.NW;
+            int I = small_div(idx, p.NW), J = idx - I * p.NW;
             eval_rhs_pair_3pt(p, cu, cv, I, J, mu, ru + idx, rv + idx);
         }
     } else {
         for (int idx = tid; idx < 2 * nn2; idx += nthr) {
             int f = idx >= nn2;
             int r = idx - f * nn2;
-            int I = r / p.NW, J = r - I * p.NW;
+            int I = small_div(r, p.NW), J = r - I * p.NW;
             ru[idx] = p.dt * eval_rhs(p, f ? p.rhs_v : p.rhs_u, f ? cv : cu, cu, cv, I, J, mu);   // rv follows ru
         }
     }

@@ -137,12 +137,12 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
     if (!producer) {
         if (p.adv_n == 2 && p.diff_n == 3) {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = idx / p.NW, J = idx - I * p.NW;
+                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
                 rf[idx] = eval_rhs_3pt(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         } else {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = idx / p.NW, J = idx - I * p.NW;
+                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
                 rf[idx] = p.dt * eval_rhs(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         }

@@ -92,7 +92,7 @@ __device__ __forceinline__ void gather_coarse(const CoarseParams& p, const float
             if (idx < hi) {
                 const int g = idx >= nn2;
                 const int r = idx - g * nn2;
-                const int I = r / p.NW, J = r - I * p.NW;
+                const int I = small_div(r, p.NW), J = r - I * p.NW;
                 tp[k] = bilinear_tap(p, I, J);
                 const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
                 a[k] = ld(q);
@@ -238,12 +238,12 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     if (!producer) {
         if (p.adv_n == 2 && p.diff_n == 3) {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = idx / p.NW, J = idx - I * p.NW;
+                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
                 rf[idx] = eval_rhs_3pt(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         } else {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = idx / p.NW, J = idx - I * p.NW;
+                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
                 rf[idx] = p.dt * eval_rhs(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         }

@@ -76,7 +76,7 @@ constexpr int kGatherBatch = 5;                     // coarse points per thread 
 // of kGatherBatch points per thread are all in flight before the first is used; zero-weight
 // taps are skipped (exact decimation for 257 -> 33).  KEEP: tag the loads L2::evict_last
 // because the same sectors are streamed again a few microseconds later.
-template <bool KEEP>
+template <bool KEEP, bool FASTDIV = true>
 __device__ __forceinline__ void gather_coarse(const CoarseParams& p, const float* __restrict__ ub, size_t plane, int FW,
                                               int lo, int hi, float* dst, int tid, int nthr) {
     const int nn2 = p.NH * p.NW;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void gather_coarse(const CoarseParams& p, const float
             if (idx < hi) {
                 const int g = idx >= nn2;
                 const int r = idx - g * nn2;
-                const int I = small_div(r, p.NW), J = r - I * p.NW;
+                const int I = FASTDIV ? small_div(r, p.NW) : r / p.NW, J = r - I * p.NW;
                 tp[k] = bilinear_tap(p, I, J);
                 const float* q = ub + g * plane + (size_t)tp[k].i0 * FW + tp[k].j0;
                 a[k] = ld(q);
@@ -154,6 +154,10 @@ template <int MODE, int FWC, bool HAS_NN>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
                           const float* u_end) {
+    // Index splits in the per-coarse-point phases go through small_div (fp32 reciprocal) except in the memory-bound
+    // update with the network operand: there the shorter sequence changes ptxas' allocation under the 56-register
+    // cap (12 bytes of spills in the band loop, 0.485 -> 0.494 ms) while the issue-bound modes gain 2-10 %.
+    constexpr bool FASTDIV = !(MODE == MODE_UPDATE && HAS_NN);
     extern __shared__ float4 smem4[];
     float4* roww = smem4;                                       // [FH] H-pass weights
     int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
@@ -229,7 +233,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         // a purely diffusive right-hand side never reads the other field
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-        gather_coarse<true>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
+        gather_coarse<true, FASTDIV>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
         build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
@@ -238,12 +242,12 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     if (!producer) {
         if (p.adv_n == 2 && p.diff_n == 3) {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
+                const int I = FASTDIV ? small_div(idx, p.NW) : idx / p.NW, J = idx - I * p.NW;
                 rf[idx] = eval_rhs_3pt(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         } else {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
-                const int I = small_div(idx, p.NW), J = idx - I * p.NW;
+                const int I = FASTDIV ? small_div(idx, p.NW) : idx / p.NW, J = idx - I * p.NW;
                 rf[idx] = p.dt * eval_rhs(p, rid, f ? cv : cu, cu, cv, I, J, mu);
             }
         }

@@ -16,8 +16,10 @@ per rank (``dist.shard_file``) unless ``--gather``.
 from __future__ import annotations
 
 import argparse
+import json
 import math
 import os
+import time
 from typing import Optional
 
 import torch
@@ -65,7 +67,10 @@ class SnapshotWriter:
         self.stage[:, 1].copy_(v.reshape(self.stage[:, 1].shape))
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
-            self.host[:, self.count].copy_(self.stage, non_blocking=True)
+            # one contiguous copy per sample: host[:, count] as a whole is strided over T, and a strided
+            # device-to-host copy_ goes through a pageable temporary and blocks (10x slower than the solver)
+            for k in range(self.host.shape[0]):
+                self.host[k, self.count].copy_(self.stage[k], non_blocking=True)
             self.done.record(self.side)
         self.count += 1
 
@@ -77,9 +82,11 @@ class SnapshotWriter:
 def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.025, mu_hi: float = 0.065,
              steps: int = 20001, every: int = 200, seed: int = 10, mode: str = "as_written",
              endpoint: bool = True, dt: float = 1e-4, dx: float = 0.0125, device: Optional[torch.device] = None,
-             rank: Optional[int] = None, world_size: Optional[int] = None, graph: bool = True) -> torch.Tensor:
+             rank: Optional[int] = None, world_size: Optional[int] = None, graph: bool = True,
+             timings: Optional[dict] = None) -> torch.Tensor:
     """This rank's shard of the dataset as a pinned host tensor [b, T, 2, mesh, mesh].
     Defaults are the reference's (5 nu x 20 ICs, 257^2, 20 001 steps, snapshot every 200)."""
+    t_begin = time.perf_counter()
     if rank is None or world_size is None:
         rank, world_size = D.world()
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -95,8 +102,15 @@ def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.
     T = len(range(0, steps, every))
     writer = SnapshotWriter(b, T, mesh, mesh, device)
     solver = FineBurgers(dt=dt, dx=dx, dy=dx, mode=mode, endpoint=endpoint)
+    if timings is not None:
+        torch.cuda.synchronize(device)
+        timings["setup_seconds"] = time.perf_counter() - t_begin       # ICs + pinned host tensor (page pinning)
+        t_begin = time.perf_counter()
     solver.run(u0, v0, mu, steps, every=every, graph=graph, sink=writer)
-    return writer.finish()
+    out = writer.finish()
+    if timings is not None:
+        timings["solve_seconds"] = time.perf_counter() - t_begin       # time stepping + snapshot D2H
+    return out
 
 
 def main(argv=None) -> None:
@@ -113,6 +127,7 @@ def main(argv=None) -> None:
     ap.add_argument("--mode", default="as_written", choices=["as_written", "intended"])
     ap.add_argument("--true-periodic", action="store_true", help="grid without the duplicated endpoint")
     ap.add_argument("--gather", action="store_true", help="gather all shards into one file on rank 0")
+    ap.add_argument("--no-save", action="store_true", help="generate and time only (throughput runs)")
     a = ap.parse_args(argv)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -120,9 +135,32 @@ def main(argv=None) -> None:
     if ws > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, ws = D.world()
+    if ws > 1:
+        torch.distributed.barrier(device_ids=[local])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tm = {}
     data = generate(a.mesh, a.para, a.repeat, a.mu_lo, a.mu_hi, a.steps, a.every, a.seed, a.mode,
-                    not a.true_periodic)
-    if a.gather and ws > 1:
+                    not a.true_periodic, timings=tm)
+    torch.cuda.synchronize()
+    sec = torch.tensor([time.perf_counter() - t0, tm["setup_seconds"], tm["solve_seconds"]], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        torch.distributed.all_reduce(sec, op=torch.distributed.ReduceOp.MAX)      # slowest rank
+    if rank == 0:
+        P = a.para * a.repeat
+        sec, setup, solve = sec.tolist()
+        print(json.dumps({"datagen": f"{P} samples x {a.mesh}^2 x {a.steps} steps, snapshot every {a.every} ({a.mode})",
+                          "n_gpus": ws, "seconds": sec, "setup_seconds": setup, "solve_seconds": solve,
+                          "samples_per_s": P / sec,
+                          "gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / sec / 1e9,
+                          "solve_gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / solve / 1e9,
+                          "snapshot_bytes": data.numel() * 4 * ws,
+                          "note": "max over ranks; setup = initial conditions + pinned host tensor (page pinning), "
+                                  "solve = time stepping with snapshot D2H on a side stream; file write excluded"}),
+              flush=True)
+    if a.no_save:
+        pass
+    elif a.gather and ws > 1:
         full = D.gather_shards(data.cuda(), a.para * a.repeat)
         if rank == 0:
             torch.save({"u": full.cpu()}, a.out)

@@ -61,8 +61,9 @@ class SnapshotWriter:
 
     NBUF = 2
 
-    def __init__(self, B: int, T: int, H: int, W: int, device):
-        self.host = torch.empty((B, T, 2, H, W), dtype=torch.float32)
+    def __init__(self, B: int, T: int, H: int, W: int, device, keep: bool = True):
+        self.keep = keep                                   # False: snapshots are dropped once they have landed (throughput runs)
+        self.host = torch.empty((B, T if keep else 0, 2, H, W), dtype=torch.float32)
         self.stage = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
         self.pin = [torch.empty((B, 2, H, W), dtype=torch.float32, pin_memory=True) for _ in range(self.NBUF)]
         self.free = [threading.Event() for _ in range(self.NBUF)]
@@ -85,7 +86,8 @@ class SnapshotWriter:
                     return
                 k, c, landed = job
                 landed.synchronize()                       # the D2H into pin[k] has completed
-                self.host[:, c].copy_(self.pin[k])
+                if self.keep:
+                    self.host[:, c].copy_(self.pin[k])
                 self.free[k].set()
         except BaseException as exc:                       # surfaced by finish()
             self.error = exc
@@ -114,14 +116,14 @@ class SnapshotWriter:
         self.thread.join()
         if self.error is not None:
             raise self.error
-        return self.host[:, :self.count]
+        return self.host[:, :self.count] if self.keep else self.host
 
 
 def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.025, mu_hi: float = 0.065,
              steps: int = 20001, every: int = 200, seed: int = 10, mode: str = "as_written",
              endpoint: bool = True, dt: float = 1e-4, dx: float = 0.0125, device: Optional[torch.device] = None,
              rank: Optional[int] = None, world_size: Optional[int] = None, graph: bool = True,
-             timings: Optional[dict] = None) -> torch.Tensor:
+             timings: Optional[dict] = None, keep: bool = True) -> torch.Tensor:
     """This rank's shard of the dataset as a host tensor [b, T, 2, mesh, mesh].
     Defaults are the reference's (5 nu x 20 ICs, 257^2, 20 001 steps, snapshot every 200)."""
     t_begin = time.perf_counter()
@@ -138,7 +140,7 @@ def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.
     u0 = fourier_initial_condition(coef[:, 0], mesh, device)
     v0 = fourier_initial_condition(coef[:, 1], mesh, device)
     T = len(range(0, steps, every))
-    writer = SnapshotWriter(b, T, mesh, mesh, device)
+    writer = SnapshotWriter(b, T, mesh, mesh, device, keep=keep)
     solver = FineBurgers(dt=dt, dx=dx, dy=dx, mode=mode, endpoint=endpoint)
     if timings is not None:
         torch.cuda.synchronize(device)
@@ -166,6 +168,9 @@ def main(argv=None) -> None:
     ap.add_argument("--true-periodic", action="store_true", help="grid without the duplicated endpoint")
     ap.add_argument("--gather", action="store_true", help="gather all shards into one file on rank 0")
     ap.add_argument("--no-save", action="store_true", help="generate and time only (throughput runs)")
+    ap.add_argument("--discard", action="store_true",
+                    help="drop every snapshot once it has landed in pinned host memory (implies --no-save): "
+                         "throughput of solver + D2H without the host-side accumulation")
     a = ap.parse_args(argv)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -173,13 +178,16 @@ def main(argv=None) -> None:
     if ws > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, ws = D.world()
+    # the drain thread's copies share the host cores with the other ranks of the node
+    local_ws = int(os.environ.get("LOCAL_WORLD_SIZE", str(ws)))
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, local_ws)))
     if ws > 1:
         torch.distributed.barrier(device_ids=[local])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     tm = {}
     data = generate(a.mesh, a.para, a.repeat, a.mu_lo, a.mu_hi, a.steps, a.every, a.seed, a.mode,
-                    not a.true_periodic, timings=tm)
+                    not a.true_periodic, timings=tm, keep=not a.discard)
     torch.cuda.synchronize()
     sec = torch.tensor([time.perf_counter() - t0, tm["setup_seconds"], tm["solve_seconds"]], dtype=torch.float64, device="cuda")
     if ws > 1:
@@ -192,11 +200,12 @@ def main(argv=None) -> None:
                           "samples_per_s": P / sec,
                           "gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / sec / 1e9,
                           "solve_gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / solve / 1e9,
-                          "snapshot_bytes": data.numel() * 4 * ws,
+                          "snapshots": "discarded after D2H" if a.discard else "kept in host memory",
+                          "host_threads_per_rank": torch.get_num_threads(),
                           "note": "max over ranks; setup = initial conditions + pinned staging buffers, "
                                   "solve = time stepping, snapshot D2H on a side stream and the drain into the host tensor; file write excluded"}),
               flush=True)
-    if a.no_save:
+    if a.no_save or a.discard:
         pass
     elif a.gather and ws > 1:
         full = D.gather_shards(data.cuda(), a.para * a.repeat)

@@ -119,12 +119,31 @@ class SnapshotWriter:
         return self.host[:, :self.count] if self.keep else self.host
 
 
+class DeviceSink:
+    """Snapshots stay in HBM as ``[B, T, 2, H, W]`` (cfg 4: 64 samples x 101 snapshots x 1025^2 = 54 GB of the
+    180 GB) -- the form ``PdeDataset`` trains from; no host traffic while the solver runs."""
+
+    def __init__(self, B: int, T: int, H: int, W: int, device):
+        self.data = torch.empty((B, T, 2, H, W), dtype=torch.float32, device=device)
+        self.count = 0
+
+    def __call__(self, i: int, u: torch.Tensor, v: torch.Tensor) -> None:
+        B, _, _, H, W = self.data.shape
+        self.data[:, self.count, 0].copy_(u.reshape(B, H, W))
+        self.data[:, self.count, 1].copy_(v.reshape(B, H, W))
+        self.count += 1
+
+    def finish(self) -> torch.Tensor:
+        return self.data[:, :self.count]
+
+
 def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.025, mu_hi: float = 0.065,
              steps: int = 20001, every: int = 200, seed: int = 10, mode: str = "as_written",
              endpoint: bool = True, dt: float = 1e-4, dx: float = 0.0125, device: Optional[torch.device] = None,
              rank: Optional[int] = None, world_size: Optional[int] = None, graph: bool = True,
-             timings: Optional[dict] = None, keep: bool = True) -> torch.Tensor:
-    """This rank's shard of the dataset as a host tensor [b, T, 2, mesh, mesh].
+             timings: Optional[dict] = None, keep: bool = True, on_device: bool = False) -> torch.Tensor:
+    """This rank's shard of the dataset as a host tensor [b, T, 2, mesh, mesh] (``on_device``: a CUDA tensor,
+    snapshots never leave HBM).
     Defaults are the reference's (5 nu x 20 ICs, 257^2, 20 001 steps, snapshot every 200)."""
     t_begin = time.perf_counter()
     if rank is None or world_size is None:
@@ -140,7 +159,7 @@ def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.
     u0 = fourier_initial_condition(coef[:, 0], mesh, device)
     v0 = fourier_initial_condition(coef[:, 1], mesh, device)
     T = len(range(0, steps, every))
-    writer = SnapshotWriter(b, T, mesh, mesh, device, keep=keep)
+    writer = DeviceSink(b, T, mesh, mesh, device) if on_device else SnapshotWriter(b, T, mesh, mesh, device, keep=keep)
     solver = FineBurgers(dt=dt, dx=dx, dy=dx, mode=mode, endpoint=endpoint)
     if timings is not None:
         torch.cuda.synchronize(device)
@@ -149,6 +168,7 @@ def generate(mesh: int = 257, para: int = 5, repeat: int = 20, mu_lo: float = 0.
     solver.run(u0, v0, mu, steps, every=every, graph=graph, sink=writer)
     out = writer.finish()
     if timings is not None:
+        torch.cuda.synchronize(device)
         timings["solve_seconds"] = time.perf_counter() - t_begin       # time stepping + snapshot D2H
     return out
 
@@ -167,6 +187,8 @@ def main(argv=None) -> None:
     ap.add_argument("--mode", default="as_written", choices=["as_written", "intended"])
     ap.add_argument("--true-periodic", action="store_true", help="grid without the duplicated endpoint")
     ap.add_argument("--gather", action="store_true", help="gather all shards into one file on rank 0")
+    ap.add_argument("--device-sink", action="store_true",
+                    help="keep the snapshots in HBM while the solver runs (one device-to-host copy before saving)")
     ap.add_argument("--no-save", action="store_true", help="generate and time only (throughput runs)")
     ap.add_argument("--discard", action="store_true",
                     help="drop every snapshot once it has landed in pinned host memory (implies --no-save): "
@@ -187,7 +209,7 @@ def main(argv=None) -> None:
     t0 = time.perf_counter()
     tm = {}
     data = generate(a.mesh, a.para, a.repeat, a.mu_lo, a.mu_hi, a.steps, a.every, a.seed, a.mode,
-                    not a.true_periodic, timings=tm, keep=not a.discard)
+                    not a.true_periodic, timings=tm, keep=not a.discard, on_device=a.device_sink)
     torch.cuda.synchronize()
     sec = torch.tensor([time.perf_counter() - t0, tm["setup_seconds"], tm["solve_seconds"]], dtype=torch.float64, device="cuda")
     if ws > 1:
@@ -200,13 +222,15 @@ def main(argv=None) -> None:
                           "samples_per_s": P / sec,
                           "gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / sec / 1e9,
                           "solve_gpoint_updates_per_s": P * 2 * a.mesh * a.mesh * a.steps / solve / 1e9,
-                          "snapshots": "discarded after D2H" if a.discard else "kept in host memory",
+                          "snapshots": "kept in HBM" if a.device_sink else "discarded after D2H" if a.discard else "kept in host memory",
                           "host_threads_per_rank": torch.get_num_threads(),
                           "note": "max over ranks; setup = initial conditions + pinned staging buffers, "
                                   "solve = time stepping, snapshot D2H on a side stream and the drain into the host tensor; file write excluded"}),
               flush=True)
     if a.no_save or a.discard:
         pass
+    elif a.device_sink and not (a.gather and ws > 1):
+        torch.save({"u": data.cpu()}, D.shard_file(a.out, rank, ws))
     elif a.gather and ws > 1:
         full = D.gather_shards(data.cuda(), a.para * a.repeat)
         if rank == 0:

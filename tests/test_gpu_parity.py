@@ -517,6 +517,9 @@ def test_datagen_sharding_snapshots_and_oracle(pk):
     assert torch.equal(one, two)
     nog = datagen.generate(rank=0, world_size=1, graph=False, **kw)
     assert torch.equal(one, nog)
+    dev = datagen.generate(rank=0, world_size=1, on_device=True, **kw)          # snapshots kept in HBM
+    assert dev.is_cuda and torch.equal(one, dev.cpu())
+    assert datagen.generate(rank=0, world_size=1, keep=False, **kw).shape[1] == 0   # throughput mode: nothing kept
     coef = D.fourier_coefficients(10, 0, 6)
     u0 = datagen.fourier_initial_condition(coef[:, 0], 65, "cuda").cpu()
     v0 = datagen.fourier_initial_condition(coef[:, 1], 65, "cuda").cpu()

@@ -19,8 +19,12 @@ point-update = one fp32 value of one field advanced one step.
                 H2D of u and nn_out, kernel, D2H of u_next, inside the timed region.
 * roofline   -- HBM bound: 12 B per point-update (read u, read nn_out, write u_next)
                 / measured launch time, against MEASURED_PEAKS.json.
-* cpu_baseline -- the CPU oracle (oracle/ppnn_oracle.py, the reference's ATen op
-                sequence) on a bounded sample of the same workload on this host's cores.
+* cpu_baseline -- the reference's own modules (operators.py / rhs.py / utility/utils.py staged
+                byte-for-byte in oracle/_ref by the build container; kind "reference") on a bounded
+                sample of the same workload on this host's cores; the oracle port
+                (oracle/ppnn_oracle.py, kind "port") only if nothing was staged.
+* parity     -- after the timed loop (outside it) 4 samples of the B-sample output are recomputed
+                by that CPU reference and compared (rel-L2, max-abs / max|ref|).
 Multi-GPU: samples are independent, so ranks own disjoint shards of the batch and there
 is no data-path collective (weak scaling: B per GPU fixed).
 """
@@ -38,7 +42,7 @@ sys.path.insert(0, ROOT)
 CASE = dict(fine=257, coarse=49, rhsu="rdpu", rhsv="rdpv", dt=0.002, length=6.4,
             paralow=0.2, parahigh=1.3, num_para=12)
 B_PER_GPU = 1920            # 12 mu x 16 ICs x 10 time levels: 1/10 of the train2D.py:121 precompute batch
-BYTES_PER_POINT = 12        # read u + read nn_out + write u_next
+BYTES_PER_POINT = 12        # nominal: read u + read nn_out + write u_next (nn_out is (F-1)^2: see algorithmic_bytes)
 METRIC = "fused_pde_step_point_updates_per_s"
 UNIT = "Gpoint-updates/s"
 
@@ -133,29 +137,56 @@ class ClockSampler:
         return out
 
 
+def algorithmic_bytes(B):
+    """Compulsory HBM traffic of one update launch: read u [B,2,F,F], read nn_out [B,2,F-1,F-1], write u_next."""
+    F = CASE["fine"]
+    return 4 * (2 * F * F + (F - 1) * (F - 1)) * 2 * B
+
+
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_oracle_step_fn(B):
-    """Bounded sample of the workload on the host cores, through the oracle port."""
+def cpu_update_fn():
+    """``(update(u, mu, nn, outmean, outstd) -> u_next, kind, description)`` on the CPU: the staged
+    reference modules bound as train2D.py:66-79,235-238 does, else the oracle port."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ppnn_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
+    args = (CASE["fine"], CASE["coarse"], CASE["rhsu"], CASE["rhsv"], CASE["dt"], CASE["length"])
+    import ref_closures as R
+    if R.available():
+        step = R.RefCoarseStep(*args)
+
+        def update(u, mu, nn, om, os_):
+            with torch.no_grad():
+                return step.update(u, mu, nn, om, os_)
+        return update, "reference", ("the reference's own operators.py / rhs.py / utility/utils.py (oracle/_ref, unmodified), "
+                                     "bound as train2D.py:66-79,235-238")
+    import ppnn_oracle as O
+    step = O.CoarseStep(*args)
+
+    def update(u, mu, nn, om, os_):
+        with torch.no_grad():
+            return O.ppnn_update(u, step.pde_du(u, mu), nn, om, os_)
+    return update, "port", "oracle/ppnn_oracle.py (the reference's ATen op sequence: interpolate/conv2d/cat)"
+
+
+def cpu_oracle_step_fn(B):
+    """Bounded sample of the workload on the host cores."""
+    import torch
+    update, kind, desc = cpu_update_fn()
     F = CASE["fine"]
     u = synth_fields(B, F, torch.device("cpu"), 10)
     mu = make_mu(B, torch.device("cpu"))
     nn = torch.randn(B, 2, F - 1, F - 1, generator=torch.Generator().manual_seed(11))
     om = torch.tensor(STATS["outmean"]).reshape(1, 2, 1, 1)
     os_ = torch.tensor(STATS["outstd"]).reshape(1, 2, 1, 1)
-    step = O.CoarseStep(F, CASE["coarse"], CASE["rhsu"], CASE["rhsv"], CASE["dt"], CASE["length"])
 
     def run():
-        with torch.no_grad():
-            return O.ppnn_update(u, step.pde_du(u, mu), nn, om, os_)
-    return run, B * 2 * F * F
+        return update(u, mu, nn, om, os_)
+    return run, B * 2 * F * F, kind, desc
 
 
 def time_cpu(B, min_seconds=12.0, max_reps=400):
-    run, pts = cpu_oracle_step_fn(B)
+    run, pts, kind, desc = cpu_oracle_step_fn(B)
     run()                                                   # warm-up
     t0 = time.perf_counter()
     reps = 0
@@ -163,7 +194,7 @@ def time_cpu(B, min_seconds=12.0, max_reps=400):
         run()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
-    return pts / dt / 1e9, reps, dt
+    return pts / dt / 1e9, reps, dt, kind, desc
 
 
 def run_reference(args):
@@ -172,7 +203,7 @@ def run_reference(args):
         return
     import torch
     B = args.cpu_batch
-    run, pts = cpu_oracle_step_fn(B)
+    run, pts, kind, desc = cpu_oracle_step_fn(B)
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -184,23 +215,22 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, 1, sample_of=args.batch),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{B} of {args.batch} samples per step, oracle/ppnn_oracle.py (the reference's "
-                                       f"ATen op sequence: interpolate/conv2d/cat) on {cores} torch threads"},
+            "config": workload_config(args.batch, max(args.gpus, 1)),
+            "cpu_sample_per_step": B,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{B} of {args.batch} samples per step (the metric is per point-update, so the "
+                                       f"slice is comparable), {desc}, on {cores} torch threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(B, n, sample_of=None):
+def workload_config(B, n):
     c = {"workload": "cases/RD_pPDE.yaml fused step: u_next = padBC_rd(nn*outstd+outmean) + u + pde_du(u,mu)",
          "fine": CASE["fine"], "coarse": CASE["coarse"], "rhs": [CASE["rhsu"], CASE["rhsv"]],
          "dt": CASE["dt"], "length": CASE["length"], "batch_per_gpu": B, "global_batch": B * n,
          "parallelism": f"batch-sharded x{n}, no data-path collective",
          "l2": "inputs (3.0 GB per GPU) exceed the 126 MB L2; no flush needed"}
-    if sample_of:
-        c["sample_of_batch"] = sample_of
     return c
 
 
@@ -264,6 +294,21 @@ def run_ours(args):
     ms = timed(kernel_step, args.steps, max(args.warmup, 3))
     value = world * pts / (ms * 1e-3) / 1e9
 
+    # ---- parity of what was just timed (outside the timed region): 4 samples spread over the batch,
+    # i.e. over first / middle / last CTA waves, recomputed by the CPU reference
+    parity = None
+    if rank == 0:
+        idx = sorted({0, B // 3, (2 * B) // 3, B - 1})
+        sel = torch.tensor(idx, device=dev)
+        update, pkind, _ = cpu_update_fn()
+        ref = update(u[sel].cpu(), mu[sel].cpu(), nn[sel].cpu(), torch.tensor(STATS["outmean"]).reshape(1, 2, 1, 1),
+                     torch.tensor(STATS["outstd"]).reshape(1, 2, 1, 1)).double()
+        got = out[sel].cpu().double()
+        parity = {"rel_l2": ((got - ref).norm() / ref.norm()).item(),
+                  "rel_max": ((got - ref).abs().max() / ref.abs().max()).item(),
+                  "samples": len(idx), "sample_indices": idx, "against": pkind, "tolerance": 1e-5}
+        parity["ok"] = bool(parity["rel_l2"] <= 1e-5 and parity["rel_max"] <= 1e-5)
+
     # ---- e2e: pinned host buffers -> HostStepPipeline (H2D / kernel / D2H on three streams) ----
     nchunk = 8
     u_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True).copy_(u)
@@ -279,7 +324,7 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, e2e_steps, 1)
     e2e_value = world * pts / (ms_e2e * 1e-3) / 1e9
     torch.cuda.synchronize()
-    e2e_ok = bool(torch.equal(out_h[:4], out[:4].cpu()))
+    e2e_ok = bool(torch.equal(out_h, out.cpu()))             # the WHOLE batch: every chunk incl. the ragged last one
     h2d = (u.numel() + nn.numel()) * 4
     d2h = u.numel() * 4
 
@@ -388,7 +433,7 @@ def run_ours(args):
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         peak = 6650.0
-    achieved = BYTES_PER_POINT * pts / (ms * 1e-3) / 1e9
+    achieved = algorithmic_bytes(B) / (ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("coarse_step_update_bytes_per_launch")
@@ -405,16 +450,19 @@ def run_ours(args):
                            "host buffers, 8 chunks through separate H2D / kernel / D2H streams (ring of 3 device buffer sets)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "coarse_step_staged_kernel<MODE_UPDATE, 257, HAS_NN>",
-                         "algorithmic_bytes_per_launch": BYTES_PER_POINT * pts,
-                         "bytes_per_point_update": BYTES_PER_POINT},
+                         "traffic": traffic, "traffic_source": "static: ncu --set full capture of this kernel at this shape "
+                                                               "(profiles/traffic.json), not measured in this run",
+                         "peak_source": peak_src, "kernel": "coarse_step_staged_kernel<MODE_UPDATE, 257, HAS_NN>",
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(B),
+                         "bytes_per_point_update": algorithmic_bytes(B) / pts},
+            "parity": parity,
             "extras": extras}
     if world == 1 and not args.no_cpu:
-        v, reps, dt = time_cpu(args.cpu_batch)
+        v, reps, dt, kind, desc = time_cpu(args.cpu_batch)
         import torch as _t
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": kind,
                                 "sample": f"{args.cpu_batch} of {B} samples x {reps} reps ({dt:.2f} s each), "
-                                          "oracle/ppnn_oracle.py (reference ATen op sequence) on all host threads"}
+                                          f"{desc}, on all host threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

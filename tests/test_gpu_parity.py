@@ -247,6 +247,32 @@ def test_pde_du_small_grads_update_rollout_against_reference_golden(pk, case):
     assert_parity(roll.cpu(), g[f"{case}/rollout5"], TOL, case + " rollout5")
 
 
+@pytest.mark.parametrize("case", ["rd_p", "burgers_p"])
+def test_headline_update_and_inputs_against_reference_golden(pk, case):
+    """The instantiations bench.py times -- coarse_step_staged_kernel<MODE_UPDATE, 257, HAS_NN> and
+    <MODE_INPUTS, 257> -- against train2D.py:235-238 run on the reference modules at 257^2, B = 3,
+    mixed sign (tests/golden/step_257.npz); also through the allocation-free entry the bench uses and
+    at a batch position beyond the first CTA wave."""
+    g = load_golden("step_257.npz")
+    c = CASES[case]
+    L = pk["lib"]
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    u, nn, mu = g["u"].cuda(), g["nn"].cuda(), g[f"{case}/mu"].cuda()
+    ref = g[f"{case}/update"]
+    upd = step.step_update(u, mu, nn, g["outmean"], g["outstd"])
+    assert_parity(upd.cpu(), ref, TOL, case + " update")
+    # the same three samples tiled to B = 603 (> 296 resident CTAs): every copy must be bit-identical
+    reps = 201
+    ub, nb, mb = u.repeat(reps, 1, 1, 1), nn.repeat(reps, 1, 1, 1), mu.reshape(-1).repeat(reps).contiguous()
+    out = torch.empty_like(ub)
+    step.step_update_(ub, mb, nb, L.f2(g["outmean"]), L.f2(g["outstd"]), out)
+    assert torch.equal(out.reshape(reps, 3, 2, 257, 257), upd.unsqueeze(0).expand(reps, -1, -1, -1, -1))
+    un, pn, _ = step.step_inputs(u, mu, g["inmean"], g["instd"], g[f"{case}/pdemean"], g[f"{case}/pdestd"])
+    assert_parity(un[:, :, ::8, ::8].cpu(), g[f"{case}/u_norm"], TOL, case + " u_norm")
+    sd = g[f"{case}/pdestd"]
+    assert_parity(pn.cpu() * sd, g[f"{case}/pdeu_norm"] * sd, TOL, case + " pdeu_norm")
+
+
 @pytest.mark.parametrize("case", ["burgers_p", "burgers_f", "rd_f"])
 def test_step_update_adjoint(pk, case):
     """u_next = padBC_rd(nn*s+m) + u + pde_du(u): gradients to u, mu and nn."""

@@ -117,6 +117,22 @@ def test_pde_du_small_with_grads_update_rollout(case):
     assert_parity(roll, g[f"{case}/rollout5"], TOL, case + " rollout5")
 
 
+@pytest.mark.parametrize("case", ["rd_p", "burgers_p"])
+def test_headline_step_full_size(case):
+    """train2D.py:235-238 (update with a network-output operand) and :235-237 (network inputs)
+    at 257^2, B = 3 -- the shapes of the kernels bench.py times."""
+    g = load_golden("step_257.npz")
+    c = CASES[case]
+    step = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    u, mu = g["u"], g[f"{case}/mu"]
+    pde = step.pde_du(u, mu)
+    assert_parity(O.ppnn_update(u, pde, g["nn"], g["outmean"], g["outstd"]), g[f"{case}/update"], TOL, case + " update")
+    a, _, cc = O.ppnn_net_inputs(u, mu, pde, g["inmean"], g["instd"], torch.tensor(0.0), torch.tensor(1.0),
+                                 g[f"{case}/pdemean"], g[f"{case}/pdestd"])
+    assert_parity(a[:, :, ::8, ::8], g[f"{case}/u_norm"], TOL, case + " u_norm")
+    assert_parity(cc * g[f"{case}/pdestd"], g[f"{case}/pdeu_norm"] * g[f"{case}/pdestd"], TOL, case + " pdeu_norm")
+
+
 @pytest.mark.parametrize("mode", ["as_written", "intended"])
 def test_fine_solver(mode):
     g = load_golden("fine.npz")
@@ -152,3 +168,28 @@ def test_training_set_precompute(case):
         assert torch.allclose(out[k], g[f"{case}/{k}"], rtol=1e-6, atol=1e-9), k
     for k in ("u0_normd", "pdeu_normd", "du_normd", "mu_normd"):
         assert_parity(out[k], g[f"{case}/{k}"], 1e-6, f"{case}/{k}")
+
+
+def test_staged_reference_is_unmodified_and_agrees_with_golden_and_port():
+    """oracle/_ref (what bench.py's CPU legs execute, kind "reference"): byte-identical to the manifest
+    written at staging time, and its pde_du / update reproduce the golden fixture and the port."""
+    import hashlib
+    import json
+    import os
+    import ref_closures as R
+    if not R.available():
+        pytest.skip("oracle/_ref not staged")
+    man = json.load(open(os.path.join(R.HERE, "_ref", "MANIFEST.json")))["sha256"]
+    for rel, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(R.HERE, "_ref", rel), "rb").read()).hexdigest() == digest, rel
+    if os.path.isdir("/root/reference"):          # build container: the staged copy IS the reference
+        for rel, digest in man.items():
+            assert hashlib.sha256(open(os.path.join("/root/reference", rel), "rb").read()).hexdigest() == digest, rel
+    g = load_golden("step_257.npz")
+    c = CASES["rd_p"]
+    ref = R.RefCoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    with torch.no_grad():
+        upd = ref.update(g["u"], g["rd_p/mu"], g["nn"], g["outmean"], g["outstd"])
+    assert_parity(upd, g["rd_p/update"], TOL, "staged reference update")
+    port = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    assert_parity(O.ppnn_update(g["u"], port.pde_du(g["u"], g["rd_p/mu"]), g["nn"], g["outmean"], g["outstd"]), upd, TOL, "port")

@@ -311,7 +311,7 @@ static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* 
         size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + p.CW + 3) & ~3) * sizeof(int) +
                        ((size_t)((p.CW * support + 3) & ~3) + ((nn2 + 3) & ~3) + (((size_t)(p.CH + 4) * lay.apitch + 3) & ~(size_t)3) + un) * sizeof(float);
         if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 112 * 1024 &&
-            grad_u != grad_out && !getenv("PPNN_NO_TMA") && (!grad_nn || gnn_ok)) {
+            grad_u != grad_out && !PPNN_ENV_OFF("PPNN_NO_TMA") && (!grad_nn || gnn_ok)) {
             void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
             // (the network-output gradient only exists for the update, i.e. with the identity term)
             if (grad_nn && !add_identity) return PPNN_E_SHAPE;

@@ -309,7 +309,7 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     if (pl.band_rows < 1) { pl.band_rows = p.FH; pl.nband = 1; }
     // TMA-staged path: operands through a shared-memory ring (see coarse_step_staged.cuh)
     const bool nn_ok = !io.nn || (reinterpret_cast<uintptr_t>(io.nn) & 15) == 0;
-    if (pl.nchunk <= PPNN_STEP_WARPS && B < (1 << 30) && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !getenv("PPNN_NO_TMA")) {
+    if (pl.nchunk <= PPNN_STEP_WARPS && B < (1 << 30) && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !PPNN_ENV_OFF("PPNN_NO_TMA")) {
         StagedLayout lay;
         lay.ustage = MODE == MODE_PDEU ? 0 : (kStageRows * p.FW + 8 + 3) & ~3;
         lay.nstage = (MODE == MODE_UPDATE && io.nn) ? kStageRows * (p.FW - 1) : 0;

@@ -8,6 +8,15 @@
 #include <stdint.h>
 #include "../../include/ppnn_b200.h"
 
+// Kernel-selection switches for debugging (force a fallback kernel).  The shipped library reads NO
+// environment and keeps no global state: they exist only in builds with -DPPNN_DEBUG_ENV.
+#ifdef PPNN_DEBUG_ENV
+#include <stdlib.h>
+#define PPNN_ENV_OFF(name) (getenv(name) != nullptr)
+#else
+#define PPNN_ENV_OFF(name) false
+#endif
+
 namespace ppnn {
 
 constexpr int kMaxTaps = 9;

@@ -326,7 +326,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
 template <int HL, int MODE, int WC>
 static int launch_fine_ep(const FineParams& p, int B, void* stream, bool* used) {
     *used = false;
-    if (getenv("PPNN_NO_TMA") || getenv("PPNN_NO_EP")) return PPNN_OK;
+    if (PPNN_ENV_OFF("PPNN_NO_TMA") || PPNN_ENV_OFF("PPNN_NO_EP")) return PPNN_OK;
     // rows that the aligned tile kernel does not take; whole rows must fit a ring row.  From the reference's
     // own 257^2 up (4 CTAs of 4 + 1 consumer warps per SM) this kernel beats the register-window one
     // (257^2: 0.134 -> 0.124 ms at B = 512, intended mode 0.227 -> 0.174 ms); narrower meshes stay there.

@@ -240,7 +240,7 @@ fine_step_tile_kernel(const FineParams p, const FineTilePlan pl) {
 template <int HL, int MODE>
 static int launch_fine_tile(const FineParams& p, int B, void* stream, bool* used) {
     *used = false;
-    if (getenv("PPNN_NO_TMA") || getenv("PPNN_NO_TILE")) return PPNN_OK;
+    if (PPNN_ENV_OFF("PPNN_NO_TMA") || PPNN_ENV_OFF("PPNN_NO_TILE")) return PPNN_OK;
     // true periodic, 16-byte aligned rows, too wide for whole rows in the ring
     if (p.PW != p.W || p.PH != p.H || p.W % 8 != 0 || p.W < 256 || p.H < 2 * kTmaRows) return PPNN_OK;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.v);

@@ -267,14 +267,25 @@ extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
     p.dx = dx; p.dy = dy; p.dx2 = dx2; p.dy2 = dy2;
     p.rdx = 1.f / dx; p.rdy = 1.f / dy; p.rdx2 = 1.f / dx2; p.rdy2 = 1.f / dy2;
     p.total = (long)B * H * W;
-    if (B > 65535 || (H + kRhsRows - 1) / kRhsRows > 65535) return PPNN_E_SHAPE;
+    if ((H + kRhsRows - 1) / kRhsRows > 65535) return PPNN_E_SHAPE;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (p.K) {
-    case 1: return launch_rhs2d<1>(p, B, s);
-    case 3: return launch_rhs2d<3>(p, B, s);
-    case 5: return launch_rhs2d<5>(p, B, s);
-    case 7: return launch_rhs2d<7>(p, B, s);
-    case 9: return launch_rhs2d<9>(p, B, s);
+    // samples ride on gridDim.z (<= 65535): larger batches go out as several launches
+    const size_t axs = (size_t)(H + 2 * halo) * W, ays = (size_t)H * (W + 2 * halo), os = (size_t)H * W;
+    for (long b0 = 0; b0 < B; b0 += 65535) {
+        const int n = (int)(B - b0 < 65535 ? B - b0 : 65535);
+        p.u1 = u1 + b0 * os; p.v1 = v1 + b0 * os; p.mu = mu + b0; p.ax = ax + b0 * axs; p.ay = ay + b0 * ays;
+        p.out = out + b0 * os;
+        p.total = (long)n * H * W;
+        int st;
+        switch (p.K) {
+        case 1: st = launch_rhs2d<1>(p, n, s); break;
+        case 3: st = launch_rhs2d<3>(p, n, s); break;
+        case 5: st = launch_rhs2d<5>(p, n, s); break;
+        case 7: st = launch_rhs2d<7>(p, n, s); break;
+        case 9: st = launch_rhs2d<9>(p, n, s); break;
+        default: return PPNN_E_HALO;
+        }
+        if (st != PPNN_OK) return st;
     }
-    return PPNN_E_HALO;
+    return PPNN_OK;
 }

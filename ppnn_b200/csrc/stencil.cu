@@ -294,13 +294,21 @@ static int launch_bwd(const StencilBwdParams& p, cudaStream_t s) {
     }                                                          \
     return PPNN_E_SCHEME;
 
+static int stencil_fwd_chunk(const StencilParams& p, long planes, int axis, int K, bool up, cudaStream_t s) {
+#define CALL_FWD(K, U) launch_fwd<K, U>(p, planes, axis, s)
+    PPNN_DISPATCH_K(K, up, CALL_FWD)
+#undef CALL_FWD
+}
+
+constexpr long kMaxGridZ = 65535;
+
 static int check_geometry(long planes, int Hin, int Win, int axis, int K, int* Hout, int* Wout) {
     if (planes < 0 || Hin < 1 || Win < 1) return PPNN_E_SHAPE;
     if (axis != 2 && axis != 3) return PPNN_E_MODE;
     *Hout = axis == 2 ? Hin - K + 1 : Hin;
     *Wout = axis == 3 ? Win - K + 1 : Win;
     if (*Hout < 1 || *Wout < 1) return PPNN_E_SHAPE;
-    if (planes > 65535 || *Hout > 65535 * kRows) return PPNN_E_SHAPE;
+    if (*Hout > 65535 * kRows) return PPNN_E_SHAPE;
     return PPNN_OK;
 }
 
@@ -320,10 +328,15 @@ extern "C" int ppnn_stencil_fwd(const float* in, float* out, long planes, int Hi
     p.in = in; p.out = out; p.Hin = Hin; p.Win = Win; p.centre = accuracy;
     for (int k = 0; k < kMaxTaps; ++k) { p.a[k] = ta.c[k]; p.b[k] = scheme == PPNN_UPWIND1 ? tb.c[k] : 0.f; }
     const bool up = scheme == PPNN_UPWIND1;
-    cudaStream_t s = (cudaStream_t)stream;
-#define CALL_FWD(K, U) launch_fwd<K, U>(p, planes, axis, s)
-    PPNN_DISPATCH_K(ta.n, up, CALL_FWD)
-#undef CALL_FWD
+    // planes ride on gridDim.z (<= 65535): larger batches go out as several launches
+    for (long p0 = 0; p0 < planes; p0 += kMaxGridZ) {
+        const long n = planes - p0 < kMaxGridZ ? planes - p0 : kMaxGridZ;
+        p.in = in + (size_t)p0 * Hin * Win;
+        p.out = out + (size_t)p0 * p.Hout * p.Wout;
+        st = stencil_fwd_chunk(p, n, axis, ta.n, up, (cudaStream_t)stream);
+        if (st != PPNN_OK) return st;
+    }
+    return PPNN_OK;
 }
 
 extern "C" int ppnn_stencil_bwd(const float* grad_out, const float* in, float* grad_in,

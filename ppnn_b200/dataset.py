@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from .dist import scalar_stats
 from .fused import CoarseStep
 
 _NAMES = ("in", "pde", "out")
@@ -44,6 +45,9 @@ def upload(host: torch.Tensor, device, chunk_bytes: int = 256 << 20) -> torch.Te
     stage = [torch.empty(step, dtype=torch.float32).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
     side = torch.cuda.Stream(device)
+    # `out` was allocated on the current stream: a recycled block may still be read by kernels queued
+    # there, so the side stream must not write it before they finish
+    side.wait_stream(torch.cuda.current_stream(device))
     with torch.cuda.stream(side):
         for k, lo in enumerate(range(0, n, step)):
             hi = min(n, lo + step)
@@ -81,6 +85,9 @@ class PdeDataset(torch.utils.data.Dataset):
            window of train2D.py:84-85
     mus    one parameter per SAMPLE, [P*T] or [P*T,1,1,1] (train2D.py ``mus``)
     step   the case's CoarseStep; None = ``params.pde == False`` (no pdeu arrays)
+
+    Construction is COLLECTIVE when a process group is initialised (world size > 1): every rank of
+    ``group`` (default: the world) must build its shard, or the all-reduces of the statistics hang.
     """
 
     def __init__(self, fdata: torch.Tensor, mus: torch.Tensor, step: Optional[CoarseStep],
@@ -143,7 +150,9 @@ class PdeDataset(torch.utils.data.Dataset):
             self.pdemean, self.pdestd = mean[1].reshape(shape).to(device), std[1].reshape(shape).to(device)
         self.outmean, self.outstd = mean[2].reshape(shape).to(device), std[2].reshape(shape).to(device)
         self.mu = mu.reshape(-1, 1, 1, 1)
-        self.mumean, self.mustd = self.mu.mean(), self.mu.std()                 # train2D.py:149-150
+        # train2D.py:149-150 takes mean / std of `mus` over the WHOLE data set: with sharded trajectories
+        # the (count, sum, sum of squares) of the local parameters are all-reduced like the other statistics
+        self.mumean, self.mustd = scalar_stats(self.mu, group)
         self.mu_normd = (self.mu - self.mumean) / self.mustd                    # train2D.py:151
         self.trajectories = traj if keep_trajectories else None
 

@@ -77,6 +77,28 @@ def channel_stats(x: torch.Tensor, dims: Sequence[int] = (0, 2, 3), group=None) 
     return mean.float().reshape(shape), var.clamp_min(0).sqrt().float().reshape(shape)
 
 
+def scalar_stats(x: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Mean and unbiased standard deviation (``Tensor.mean()`` / ``Tensor.std()``, train2D.py:149-150) of
+    ALL values of the global data set from the local shard ``x``: one fp64 all-reduce of (count, sum of
+    deviations from a pivot, sum of squared deviations).  The pivot (the global maximum, itself
+    all-reduced) keeps the variance formula well conditioned when |mean| >> std.  0-d float32 results
+    on ``x``'s device."""
+    xd = x.detach().double().reshape(-1)
+    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    pivot = xd.max() if xd.numel() else torch.tensor(float("-inf"), dtype=torch.float64, device=x.device)
+    if ws > 1:
+        pivot = pivot.clone()
+        dist.all_reduce(pivot, op=dist.ReduceOp.MAX, group=group)
+    d = xd - pivot
+    buf = torch.stack((torch.tensor(float(xd.numel()), dtype=torch.float64, device=x.device), d.sum(), (d * d).sum()))
+    if ws > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    n, s1, s2 = buf[0], buf[1], buf[2]
+    mean = pivot + s1 / n
+    var = (s2 - s1 * s1 / n) / (n - 1)
+    return mean.float(), var.clamp_min(0).sqrt().float()
+
+
 def gather_shards(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
     """Concatenate the per-rank shards (possibly ragged) on rank 0 (None elsewhere)."""
     rank, ws = world()

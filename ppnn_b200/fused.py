@@ -258,8 +258,11 @@ class RolloutPlan:
     ``run(u0, nsteps)`` only replays; the capture (cuDNN autotune, allocator warm-up, graph
     instantiation) is paid once in the constructor."""
 
+    @torch.no_grad()
     def __init__(self, step: CoarseStep, net: Callable, batch: int, mu, stats: Dict[str, torch.Tensor],
                  uses_pde: bool = True, graph: bool = True, device="cuda"):
+        # inference only (train2D.py:227 `model.eval()`): never record autograd -- neither into the captured
+        # graph's pool nor across the ping-pong state buffers.  Training through the step uses `step_update`.
         self.step, self.net, self.uses_pde = step, net, uses_pde
         dev = torch.device(device)
         B = int(batch)
@@ -286,6 +289,7 @@ class RolloutPlan:
                     self.x.copy_(self.nxt)
                 self.graph = g
 
+    @torch.no_grad()
     def _one_step(self, src, dst):
         st = self.step
         if self.uses_pde:
@@ -297,6 +301,7 @@ class RolloutPlan:
             nn_out = self.net(un, self.mun)
             dst.copy_(torch.nn.functional.pad(nn_out * self.ostd_t + self.omean_t, (0, 1, 0, 1), mode="circular") + src)
 
+    @torch.no_grad()
     def run(self, u: torch.Tensor, nsteps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B,2,F,F] -> [B, nsteps, 2, F, F] (``out`` may be a preallocated result tensor)."""
         self.step._check_state(u)

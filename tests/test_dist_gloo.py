@@ -89,6 +89,12 @@ def _stats_worker(rank, world, port, tmp):
         ref_m = x.mean(dim=(1, 3))
         ref_s = x.std(dim=(1, 3))
         assert torch.allclose(mean, ref_m, rtol=1e-6, atol=1e-7) and torch.allclose(std, ref_s, rtol=1e-6)
+        # the parameter statistics of train2D.py:149-150 over RAGGED shards with different mu subsets
+        # (each rank alone would get another mean / std): every rank must see the global values
+        mus = torch.linspace(0.02, 0.07, 7).reshape(-1, 1).repeat(1, 5).reshape(-1, 1, 1, 1) + 100.0   # |mean| >> std
+        mm, ms = D.scalar_stats(mus[lo * 5:hi * 5])
+        assert torch.allclose(mm, mus.mean(), rtol=1e-7) and torch.allclose(ms, mus.std(), rtol=1e-5), (mm, ms)
+        assert not torch.allclose(mus[lo * 5:hi * 5].std(), mus.std(), rtol=1e-3)
         if rank == 0:
             open(os.path.join(tmp, "ok2"), "w").write("ok")
     finally:

@@ -94,6 +94,31 @@ def test_operator_large_and_ragged_shapes(pk):
             assert_parity(ours.cpu(), ref, TOL, f"{cls} {b}x{h}x{w}")
 
 
+def test_batches_beyond_the_grid_z_limit(pk):
+    """The reference accepts any batch size; planes ride on gridDim.z (<= 65535), so the C entry points
+    cut larger batches into several launches.  70 001 tiny planes through every Tier-A kernel family."""
+    gen = torch.Generator().manual_seed(9)
+    ops, rhs = pk["ops"], pk["rhs"]
+    b, n = 70001, 8
+    u = torch.randn(b, 1, n, n, generator=gen)
+    v = torch.randn(b, 1, n, n, generator=gen)
+    mu = torch.rand(b, 1, 1, 1, generator=gen) * 0.05 + 0.02
+    ux, uy = O.wrap_x(u), O.wrap_y(u)
+    for cls, scheme, acc, axis, x in [("d2udx2_2D", "Central2", 2, 2, ux), ("dudy_2D", "Upwind1", 1, 3, uy)]:
+        op = _make_op(ops, cls, scheme, acc)
+        xc = x.cuda().requires_grad_(True)
+        y = op(xc)
+        assert_parity(y.detach().cpu(), O.stencil2d(x, scheme, acc, axis), TOL, cls + " big batch")
+        (g,) = torch.autograd.grad(y, xc, torch.ones_like(y))
+        assert torch.isfinite(g).all() and g[-1].abs().sum() > 0
+    o = O.Ops(adv_accuracy=1, diff_accuracy=2)
+    ref = O.rhs("burgers2Dpu", u, v, mu, o, ux, uy, 0.1, 0.1, 0.01, 0.01)
+    ours = rhs.burgers2Dpu(u.cuda(), v.cuda(), mu.cuda(), ops.dudx_2D(accuracy=1), ops.dudy_2D(accuracy=1),
+                           ops.d2udx2_2D(accuracy=2), ops.d2udy2_2D(accuracy=2), ux.cuda(), uy.cuda(), 0.1, 0.1, 0.01, 0.01)
+    assert_parity(ours.cpu(), ref, TOL, "fused rhs big batch")
+    assert_parity(ours[-3:].cpu(), ref[-3:], TOL, "fused rhs big batch, last chunk")
+
+
 def test_operator_api_errors(pk):
     ops = pk["ops"]
     with pytest.raises(AssertionError):

@@ -356,7 +356,23 @@ def run_ours(args):
                                              gu.data_ptr(), gmu.data_ptr(), gnn.data_ptr(), B, L.stream()), "update bwd")
         t = timed(upd_bwd, reps, 2)
         extras["step_update_bwd"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 12, "hbm_gbs": 12 * pts / t / 1e6}
-        del gnn
+        # the same two from the coarse state the forward kernel saved (what autograd through step_update does)
+        coarse = torch.empty(B, 2, CASE["coarse"] - 1, CASE["coarse"] - 1, device=dev)
+        L.check(lib.ppnn_step_update_save(C.byref(step.cfg), u.data_ptr(), muv.data_ptr(), nn.data_ptr(), om, os_,
+                                          gu.data_ptr(), coarse.data_ptr(), B, L.stream()), "update (saving)")
+        t = timed(lambda: L.check(lib.ppnn_step_update_save(C.byref(step.cfg), u.data_ptr(), muv.data_ptr(), nn.data_ptr(), om, os_,
+                                                            gu.data_ptr(), coarse.data_ptr(), B, L.stream()), "update (saving)"), reps, 2)
+        extras["step_update_saving_coarse_state"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 12,
+                                                     "hbm_gbs": 12 * pts / t / 1e6}
+        t = timed(lambda: L.check(lib.ppnn_pde_du_bwd_saved(C.byref(step.cfg), coarse.data_ptr(), muv.data_ptr(), out.data_ptr(),
+                                                            gu.data_ptr(), gmu.data_ptr(), B, 1, L.stream()), "bwd saved"), reps, 2)
+        extras["step_adjoint_saved_state"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 8, "hbm_gbs": 8 * pts / t / 1e6}
+        t = timed(lambda: L.check(lib.ppnn_step_update_bwd_saved(C.byref(step.cfg), coarse.data_ptr(), muv.data_ptr(), out.data_ptr(),
+                                                                 os_, gu.data_ptr(), gmu.data_ptr(), gnn.data_ptr(), B, L.stream()),
+                                  "update bwd saved"), reps, 2)
+        extras["step_update_bwd_saved_state"] = {"ms": t, "gpts": world * pts / t / 1e6, "bytes_per_pt": 12,
+                                                 "hbm_gbs": 12 * pts / t / 1e6}
+        del gnn, coarse
         # training-set precompute (train2D.py:109-151): statistics pass and emit pass over (u, u_next) pairs
         part = torch.empty(B, 2, 6, dtype=torch.float64, device=dev)
         t = timed(lambda: L.check(lib.ppnn_dataset_stats(C.byref(step.cfg), u.data_ptr(), out.data_ptr(), muv.data_ptr(),

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PPNN_B200_ABI_VERSION 1
+#define PPNN_B200_ABI_VERSION 2
 
 /* ---- status codes --------------------------------------------------------- */
 #define PPNN_OK            0
@@ -137,6 +137,25 @@ int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
 int ppnn_step_update_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                          const float* grad_out, const float* outstd,
                          float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream);
+
+/* Saved-state variants for training through unrolled rollouts (autograd over src/train2D.py:66-79,
+ * 235-238).  The forward entries additionally store the restricted coarse state
+ * coarse_state [B,2,CH-1,CW-1] (= mesh_convertor.down(u)[:,:,:-1,:-1] of both fields, train2D.py:67-68;
+ * 18 KB per sample on the 257/49 mesh); coarse_state may be NULL (then they are the plain entries).
+ * The backward entries take that state INSTEAD of u: pde_du depends on u only through it, so the
+ * 528 KB state of a step need not be kept alive for the backward pass and the adjoint kernel does not
+ * re-gather it from HBM.  coarse_state must be 16-byte aligned.  Same results as the plain entries. */
+int ppnn_pde_du_fwd_save(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                         float* pdeu, float* coarse_state, int B, void* stream);
+int ppnn_step_update_save(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                          const float* nn_out, const float* outmean, const float* outstd,
+                          float* u_next, float* coarse_state, int B, void* stream);
+int ppnn_pde_du_bwd_saved(const ppnn_coarse_cfg* cfg, const float* coarse_state, const float* mu,
+                          const float* grad_out, float* grad_u, float* grad_mu,
+                          int B, int add_identity, void* stream);
+int ppnn_step_update_bwd_saved(const ppnn_coarse_cfg* cfg, const float* coarse_state, const float* mu,
+                               const float* grad_out, const float* outstd,
+                               float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream);
 
 /* Network inputs of one rollout step (src/train2D.py:235-237), fused with pde_du:
  *   u_norm    [B,2,FH-1,FW-1] = (u[:,:,:-1,:-1]      - inmean ) / instd

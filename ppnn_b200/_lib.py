@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPNN_B200_LIB") or os.path.join(_HERE, "libppnn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 E_NULL, E_SHAPE = -1, -2          # status codes of include/ppnn_b200.h used by the host code
 
 # enums of include/ppnn_b200.h
@@ -47,6 +47,11 @@ _SIGNATURES = {
     "ppnn_pde_du_fwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_int, _P]),
     "ppnn_pde_du_bwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "ppnn_step_update_bwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.POINTER(C.c_float), _P, _P, _P, C.c_int, _P]),
+    "ppnn_pde_du_fwd_save": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, C.c_int, _P]),
+    "ppnn_step_update_save": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, C.c_int, _P]),
+    "ppnn_pde_du_bwd_saved": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "ppnn_step_update_bwd_saved": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.POINTER(C.c_float), _P, _P, _P, C.c_int, _P]),
     "ppnn_step_inputs": (C.c_int, [C.POINTER(CoarseCfg), _P, _P,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -27,6 +27,7 @@ constexpr int kMaxSupport = 96;     // fine columns that can touch one coarse co
 
 struct AdjParams {
     const float* u; const float* mu; const float* g;
+    const float* coarse;   // restricted coarse state [B,2,NH,NW] saved by the forward pass, or null (then u is gathered)
     float* gu; float* gmu;
     float* gnn;        // grad of the network output [B,2,FH-1,FW-1] (padBC_rd^T of grad_out, times outstd) or null
     float os[2];       // outstd per channel
@@ -109,6 +110,7 @@ coarse_adjoint_kernel(const CoarseParams p, const AdjParams a) {
 
     // ---- phase 0: coarse state, tables, clear A ----------------------------
     for (int idx = tid; idx < 2 * nn2; idx += nthr) {
+        if (a.coarse) { cu[idx] = __ldg(a.coarse + (size_t)b * 2 * nn2 + idx); continue; }
         int f = idx >= nn2;
         int r = idx - f * nn2;
         int I = r / p.NW, J = r - I * p.NW;
@@ -268,20 +270,45 @@ coarse_adjoint_kernel(const CoarseParams p, const AdjParams a) {
 }  // namespace ppnn
 #include <cstdlib>
 #include "coarse_adjoint_staged.cuh"
+#include "coarse_adjoint_periodic.cuh"
 
 using namespace ppnn;
 
-static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+// the reference's own meshes: compile-time period of the prolongation (coarse_adjoint_periodic.cuh)
+template <int PER, int ADV>
+static int launch_adjoint_periodic(const CoarseParams& p, const AdjParams& a, int B, void* stream) {
+    PhaseWeights pw;
+    for (int r = 0; r < 16; ++r) {
+        const float s = p.suh * (float)(r < PER ? r : 0);
+        cubic_weights(s - floorf(s), pw.w[r]);
+    }
+    void (*kern)(CoarseParams, AdjParams, PhaseWeights, const float*);
+    kern = a.gnn ? coarse_adjoint_periodic_kernel<PER, ADV, true, true>
+         : a.add_identity ? coarse_adjoint_periodic_kernel<PER, ADV, true, false>
+                          : coarse_adjoint_periodic_kernel<PER, ADV, false, false>;
+    constexpr size_t smem = adjoint_periodic_smem<PER, ADV>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (a.gmu) {                                                 // the two CTAs of a sample add their halves
+        e = cudaMemsetAsync(a.gmu, 0, (size_t)B * sizeof(float), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const float* g_end = a.g + (size_t)B * 2 * kPerF * kPerF;
+    kern<<<2 * B, kAdjThreads, smem, (cudaStream_t)stream>>>(p, a, pw, g_end);
+    return launch_status();
+}
+
+static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* coarse, const float* mu,
                        const float* grad_out, float* grad_u, float* grad_mu, float* grad_nn, const float* outstd,
                        int B, int add_identity, void* stream) {
-    if (!u || !mu || !grad_out || !grad_u) return PPNN_E_NULL;
+    if ((!u && !coarse) || !mu || !grad_out || !grad_u) return PPNN_E_NULL;
     CoarseParams p;
     int st = fill_coarse_params(cfg, &p);
     if (st != PPNN_OK) return st;
     if (B < 0) return PPNN_E_SHAPE;
     if (B == 0) return PPNN_OK;
     AdjParams a;
-    a.u = u; a.mu = mu; a.g = grad_out; a.gu = grad_u; a.gmu = grad_mu; a.add_identity = add_identity;
+    a.u = u; a.coarse = coarse; a.mu = mu; a.g = grad_out; a.gu = grad_u; a.gmu = grad_mu; a.add_identity = add_identity;
     a.gnn = grad_nn; a.os[0] = outstd ? outstd[0] : 1.f; a.os[1] = outstd ? outstd[1] : 1.f;
     a.apitch = p.FW | 1;
     // fine columns whose 4-tap window can reach one coarse column: 4 / suw (+ slack)
@@ -292,6 +319,12 @@ static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* 
     // the fused network-output gradient needs the last fine column on the last coarse node (see the kernel)
     const float slast = p.suw * (float)(p.FW - 1);
     const bool gnn_ok = (p.FW - 1) % 32 == 0 && floorf(slast) == slast && (int)slast >= p.CW - 1;
+    if (grad_nn && !add_identity) return PPNN_E_SHAPE;      // the network-output gradient only exists for the update
+    if (p.FH == kPerF && p.FW == kPerF && p.CH == p.CW && grad_u != grad_out && !PPNN_ENV_OFF("PPNN_NO_PERIODIC") &&
+        (!coarse || (reinterpret_cast<uintptr_t>(coarse) & 15) == 0)) {
+        if (p.CH == 49) return launch_adjoint_periodic<16, 3>(p, a, B, stream);
+        if (p.CH == 33) return launch_adjoint_periodic<8, 1>(p, a, B, stream);
+    }
     // staged path: (sample, field) CTAs in 2-CTA clusters, TMA ring (coarse_adjoint_staged.cuh)
     {
         AdjStagedLayout lay;
@@ -313,8 +346,6 @@ static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* 
         if (lay.nchunk <= kAdjWarps && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && smem2 <= 112 * 1024 &&
             grad_u != grad_out && !PPNN_ENV_OFF("PPNN_NO_TMA") && (!grad_nn || gnn_ok)) {
             void (*kern)(CoarseParams, AdjParams, AdjStagedLayout, const float*);
-            // (the network-output gradient only exists for the update, i.e. with the identity term)
-            if (grad_nn && !add_identity) return PPNN_E_SHAPE;
             if (p.FW == 257) kern = grad_nn ? coarse_adjoint_staged_kernel<257, true, true>
                                   : add_identity ? coarse_adjoint_staged_kernel<257, true, false> : coarse_adjoint_staged_kernel<257, false, false>;
             else             kern = grad_nn ? coarse_adjoint_staged_kernel<0, true, true>
@@ -348,12 +379,29 @@ static int run_adjoint(const ppnn_coarse_cfg* cfg, const float* u, const float* 
 extern "C" int ppnn_pde_du_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                                const float* grad_out, float* grad_u, float* grad_mu,
                                int B, int add_identity, void* stream) {
-    return run_adjoint(cfg, u, mu, grad_out, grad_u, grad_mu, nullptr, nullptr, B, add_identity, stream);
+    if (!u) return PPNN_E_NULL;
+    return run_adjoint(cfg, u, nullptr, mu, grad_out, grad_u, grad_mu, nullptr, nullptr, B, add_identity, stream);
 }
 
 extern "C" int ppnn_step_update_bwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                                     const float* grad_out, const float* outstd,
                                     float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream) {
+    if (!u) return PPNN_E_NULL;
     if (grad_nn && !outstd) return PPNN_E_NULL;
-    return run_adjoint(cfg, u, mu, grad_out, grad_u, grad_mu, grad_nn, outstd, B, 1, stream);
+    return run_adjoint(cfg, u, nullptr, mu, grad_out, grad_u, grad_mu, grad_nn, outstd, B, 1, stream);
+}
+
+extern "C" int ppnn_pde_du_bwd_saved(const ppnn_coarse_cfg* cfg, const float* coarse_state, const float* mu,
+                                     const float* grad_out, float* grad_u, float* grad_mu,
+                                     int B, int add_identity, void* stream) {
+    if (!coarse_state) return PPNN_E_NULL;
+    return run_adjoint(cfg, nullptr, coarse_state, mu, grad_out, grad_u, grad_mu, nullptr, nullptr, B, add_identity, stream);
+}
+
+extern "C" int ppnn_step_update_bwd_saved(const ppnn_coarse_cfg* cfg, const float* coarse_state, const float* mu,
+                                          const float* grad_out, const float* outstd,
+                                          float* grad_u, float* grad_mu, float* grad_nn, int B, void* stream) {
+    if (!coarse_state) return PPNN_E_NULL;
+    if (grad_nn && !outstd) return PPNN_E_NULL;
+    return run_adjoint(cfg, nullptr, coarse_state, mu, grad_out, grad_u, grad_mu, grad_nn, outstd, B, 1, stream);
 }

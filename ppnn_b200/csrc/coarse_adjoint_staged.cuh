@@ -303,7 +303,8 @@ coarse_adjoint_staged_kernel(const CoarseParams p, const AdjParams a, const AdjS
     {
         // (u is not streamed by this kernel: no L2 retention hint)
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
-        gather_coarse<false>(p, ub, plane, FW, lo, hi, cu, tid, nthr);
+        if (a.coarse) { for (int idx = lo + tid; idx < hi; idx += nthr) cu[idx] = __ldg(a.coarse + (size_t)b * 2 * nn2 + idx); }
+        else gather_coarse<false>(p, ub, plane, FW, lo, hi, cu, tid, nthr);
     }
     // grad_mu partial of this field (needs only local data)
     __syncthreads();

@@ -55,6 +55,7 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, const StepPlan pl) {
         int r = idx - f * nn2;
         int I = r / p.NW, J = r - I * p.NW;
         cu[idx] = restrict_point(p, ub + f * plane, I, J);       // cv follows cu contiguously
+        if (io.coarse) io.coarse[(size_t)b * 2 * nn2 + idx] = cu[idx];   // saved for the adjoint pass
     }
     for (int i = tid; i < p.FH; i += kStepThreads) {
         float w[4]; int i0;
@@ -345,12 +346,17 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
 
 using namespace ppnn;
 
-extern "C" int ppnn_pde_du_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
-                               float* pdeu, int B, void* stream) {
+extern "C" int ppnn_pde_du_fwd_save(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                                    float* pdeu, float* coarse_state, int B, void* stream) {
     if (!u || !mu || !pdeu) return PPNN_E_NULL;
     StepIO io = {};
-    io.u = u; io.mu = mu; io.out = pdeu;
+    io.u = u; io.mu = mu; io.out = pdeu; io.coarse = coarse_state;
     return launch_step<MODE_PDEU>(cfg, io, B, stream);
+}
+
+extern "C" int ppnn_pde_du_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                               float* pdeu, int B, void* stream) {
+    return ppnn_pde_du_fwd_save(cfg, u, mu, pdeu, nullptr, B, stream);
 }
 
 extern "C" int ppnn_step_inputs(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
@@ -368,16 +374,22 @@ extern "C" int ppnn_step_inputs(const ppnn_coarse_cfg* cfg, const float* u, cons
     return launch_step<MODE_INPUTS>(cfg, io, B, stream);
 }
 
-extern "C" int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
-                                const float* nn_out, const float* outmean, const float* outstd,
-                                float* u_next, int B, void* stream) {
+extern "C" int ppnn_step_update_save(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                                     const float* nn_out, const float* outmean, const float* outstd,
+                                     float* u_next, float* coarse_state, int B, void* stream) {
     if (!u || !mu || !u_next) return PPNN_E_NULL;
     if (nn_out && (!outmean || !outstd)) return PPNN_E_NULL;
     if (u_next == u) return PPNN_E_MODE;      // planes of one sample run on different CTAs: no in-place update
     StepIO io = {};
-    io.u = u; io.mu = mu; io.nn = nn_out; io.out = u_next;
+    io.u = u; io.mu = mu; io.nn = nn_out; io.out = u_next; io.coarse = coarse_state;
     for (int c = 0; c < 2; ++c) { io.m0[c] = nn_out ? outmean[c] : 0.f; io.s0[c] = nn_out ? outstd[c] : 1.f; }
     return launch_step<MODE_UPDATE>(cfg, io, B, stream);
+}
+
+extern "C" int ppnn_step_update(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                                const float* nn_out, const float* outmean, const float* outstd,
+                                float* u_next, int B, void* stream) {
+    return ppnn_step_update_save(cfg, u, mu, nn_out, outmean, outstd, u_next, nullptr, B, stream);
 }
 
 extern "C" int ppnn_coarse_increment(const ppnn_coarse_cfg* cfg, const float* uc, const float* mu,

@@ -240,6 +240,11 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
 
     // ---- phase 2: dt * rhs of this CTA's field on the periodic coarse grid ------
     if (!producer) {
+        if (io.coarse) {                                        // own field only: the sibling CTA writes the other one
+            const float* own = f ? cv : cu;
+            float* dst = io.coarse + ((size_t)b * 2 + f) * nn2;
+            for (int idx = tid; idx < nn2; idx += kStepThreads) dst[idx] = own[idx];
+        }
         if (p.adv_n == 2 && p.diff_n == 3) {
             for (int idx = tid; idx < nn2; idx += kStepThreads) {
                 const int I = FASTDIV ? small_div(idx, p.NW) : idx / p.NW, J = idx - I * p.NW;

@@ -108,7 +108,7 @@ __device__ __forceinline__ float resample_src(float scale, int o, bool align, bo
 }
 
 // Keys cubic convolution weights, A = -0.75 (torch get_cubic_upsample_coefficients).
-__device__ __forceinline__ void cubic_weights(float t, float w[4]) {
+__host__ __device__ __forceinline__ void cubic_weights(float t, float w[4]) {
     const float A = -0.75f;
     float x;
     x = t + 1.f;  w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;

@@ -37,7 +37,10 @@ def _mu_vec(mu, B: int, device) -> torch.Tensor:
 
 
 class _PdeDuFn(torch.autograd.Function):
-    """pde_du with the hand-written adjoint (``ppnn_pde_du_bwd``)."""
+    """pde_du with the hand-written adjoint.  When a gradient will be needed the forward kernel also
+    stores the restricted coarse state (18 KB per sample on the 257/49 mesh) and the backward pass
+    runs from that (``ppnn_pde_du_bwd_saved``): pde_du depends on ``u`` only through it, so neither is
+    the 528 KB state kept alive for the backward pass nor re-gathered from HBM by the adjoint kernel."""
 
     @staticmethod
     def forward(ctx, u, mu, step: "CoarseStep"):
@@ -46,33 +49,38 @@ class _PdeDuFn(torch.autograd.Function):
         B = x.shape[0]
         muv = _mu_vec(mu, B, x.device)
         out = torch.empty_like(x)
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        coarse = torch.empty(B, 2, step.CH - 1, step.CW - 1, dtype=torch.float32, device=x.device) if want else None
         with torch.cuda.device(x.device):
-            L.check(lib.ppnn_pde_du_fwd(C.byref(step.cfg), x.data_ptr(), muv.data_ptr(), out.data_ptr(),
-                                        B, L.stream()), "ppnn_pde_du_fwd")
+            L.check(lib.ppnn_pde_du_fwd_save(C.byref(step.cfg), x.data_ptr(), muv.data_ptr(), out.data_ptr(),
+                                             L.ptr(coarse), B, L.stream()), "ppnn_pde_du_fwd")
         ctx.step = step
         ctx.mu_shape = mu.shape if isinstance(mu, torch.Tensor) else None
-        ctx.save_for_backward(x, muv)
+        ctx.state_shape = x.shape
+        if want:
+            ctx.save_for_backward(coarse, muv)
         return out
 
     @staticmethod
     def backward(ctx, g):
         lib = L.load()
-        x, muv = ctx.saved_tensors
+        coarse, muv = ctx.saved_tensors
         g = L.dev(g, "pde_du grad")
-        B = x.shape[0]
-        gu = torch.empty_like(x)
+        B = g.shape[0]
+        gu = torch.empty(ctx.state_shape, dtype=torch.float32, device=g.device)
         want_mu = ctx.mu_shape is not None and ctx.needs_input_grad[1]
-        gmu = torch.empty(B, dtype=torch.float32, device=x.device) if want_mu else None
-        with torch.cuda.device(x.device):
-            L.check(lib.ppnn_pde_du_bwd(C.byref(ctx.step.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
-                                        gu.data_ptr(), L.ptr(gmu), B, 0, L.stream()), "ppnn_pde_du_bwd")
+        gmu = torch.empty(B, dtype=torch.float32, device=g.device) if want_mu else None
+        with torch.cuda.device(g.device):
+            L.check(lib.ppnn_pde_du_bwd_saved(C.byref(ctx.step.cfg), coarse.data_ptr(), muv.data_ptr(), g.data_ptr(),
+                                              gu.data_ptr(), L.ptr(gmu), B, 0, L.stream()), "ppnn_pde_du_bwd")
         if want_mu:
             gmu = gmu.sum().reshape(ctx.mu_shape) if ctx.mu_shape.numel() == 1 and B != 1 else gmu.reshape(ctx.mu_shape)
         return gu, gmu, None
 
 
 class _StepUpdateFn(torch.autograd.Function):
-    """u_next = padBC_rd(nn*outstd + outmean) + u + pde_du(u, mu), one kernel each way."""
+    """u_next = padBC_rd(nn*outstd + outmean) + u + pde_du(u, mu), one kernel each way; the backward
+    pass runs from the coarse state saved by the forward kernel (see ``_PdeDuFn``)."""
 
     @staticmethod
     def forward(ctx, u, mu, nn_out, step: "CoarseStep", outmean, outstd):
@@ -85,39 +93,43 @@ class _StepUpdateFn(torch.autograd.Function):
             raise RuntimeError(f"network output has shape {tuple(n.shape)}, expected {(B, 2, step.FH - 1, step.FW - 1)}")
         out = torch.empty_like(x)
         m, s = (L.f2(outmean), L.f2(outstd)) if n is not None else (None, None)
+        want = any(ctx.needs_input_grad[:3])
+        coarse = torch.empty(B, 2, step.CH - 1, step.CW - 1, dtype=torch.float32, device=x.device) if want else None
         with torch.cuda.device(x.device):
-            L.check(lib.ppnn_step_update(C.byref(step.cfg), x.data_ptr(), muv.data_ptr(), L.ptr(n), m, s,
-                                         out.data_ptr(), B, L.stream()), "ppnn_step_update")
+            L.check(lib.ppnn_step_update_save(C.byref(step.cfg), x.data_ptr(), muv.data_ptr(), L.ptr(n), m, s,
+                                              out.data_ptr(), L.ptr(coarse), B, L.stream()), "ppnn_step_update")
         ctx.step = step
         ctx.mu_shape = mu.shape if isinstance(mu, torch.Tensor) else None
         ctx.has_nn = n is not None
         ctx.outstd = [float(v) for v in s] if n is not None else None
-        ctx.save_for_backward(x, muv)
+        ctx.state_shape = x.shape
+        if want:
+            ctx.save_for_backward(coarse, muv)
         return out
 
     @staticmethod
     def backward(ctx, g):
         lib = L.load()
-        x, muv = ctx.saved_tensors
+        coarse, muv = ctx.saved_tensors
         g = L.dev(g, "step_update grad")
-        B = x.shape[0]
+        B = g.shape[0]
         gu = gmu = gnn = None
         want_nn = ctx.has_nn and ctx.needs_input_grad[2]
         want_mu = ctx.mu_shape is not None and ctx.needs_input_grad[1]
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or want_nn:
-            gu = torch.empty_like(x)
-            gmu = torch.empty(B, dtype=torch.float32, device=x.device) if want_mu else None
+            gu = torch.empty(ctx.state_shape, dtype=torch.float32, device=g.device)
+            gmu = torch.empty(B, dtype=torch.float32, device=g.device) if want_mu else None
             st = ctx.step
-            gnn = torch.empty(B, 2, st.FH - 1, st.FW - 1, dtype=torch.float32, device=x.device) if want_nn else None
-            with torch.cuda.device(x.device):
+            gnn = torch.empty(B, 2, st.FH - 1, st.FW - 1, dtype=torch.float32, device=g.device) if want_nn else None
+            with torch.cuda.device(g.device):
                 # one launch: grad_u, grad_mu and the gradient of the network output
-                status = lib.ppnn_step_update_bwd(C.byref(st.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
-                                                  (C.c_float * 2)(*ctx.outstd) if want_nn else None,
-                                                  gu.data_ptr(), L.ptr(gmu), L.ptr(gnn), B, L.stream())
+                status = lib.ppnn_step_update_bwd_saved(C.byref(st.cfg), coarse.data_ptr(), muv.data_ptr(), g.data_ptr(),
+                                                        (C.c_float * 2)(*ctx.outstd) if want_nn else None,
+                                                        gu.data_ptr(), L.ptr(gmu), L.ptr(gnn), B, L.stream())
                 if status == L.E_SHAPE and want_nn:
                     # meshes outside the reference family: adjoint kernel + padBC_rd^T composed on the device
-                    L.check(lib.ppnn_pde_du_bwd(C.byref(st.cfg), x.data_ptr(), muv.data_ptr(), g.data_ptr(),
-                                                gu.data_ptr(), L.ptr(gmu), B, 1, L.stream()), "ppnn_pde_du_bwd")
+                    L.check(lib.ppnn_pde_du_bwd_saved(C.byref(st.cfg), coarse.data_ptr(), muv.data_ptr(), g.data_ptr(),
+                                                      gu.data_ptr(), L.ptr(gmu), B, 1, L.stream()), "ppnn_pde_du_bwd")
                     gnn = g[:, :, :-1, :-1].clone()
                     gnn[:, :, 0, :] += g[:, :, -1, :-1]
                     gnn[:, :, :, 0] += g[:, :, :-1, -1]

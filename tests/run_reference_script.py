@@ -10,9 +10,12 @@ reference ``src`` (for ``models``: the trainable networks stay in PyTorch), then
 matplotlib stand-in.  The script file itself is executed as ``__main__`` by ``runpy`` --
 not one byte of it is edited (the test checks its SHA-256 against ``oracle/_ref/MANIFEST.json``).
 
-One environment shim, unrelated to the hot path: the reference targets an older, unpinned
-PyTorch (environment.yml:1) and passes ``verbose=True`` to ``ReduceLROnPlateau``
-(train2D.py:189), a keyword PyTorch >= 2.7 removed; it is dropped here.
+Two environment shims, unrelated to the hot path -- the reference targets an older, unpinned
+PyTorch (environment.yml:1): (1) it passes ``verbose=True`` to ``ReduceLROnPlateau``
+(train2D.py:189), a keyword PyTorch >= 2.7 removed; it is dropped here.  (2) it indexes a CPU
+tensor with a CUDA index tensor (train2D.py:88-89, ``fdata[testIDs, 0]``), which old PyTorch
+accepted and current PyTorch rejects; on exactly that error the index is moved to the indexed
+tensor's device and the indexing retried.
 
 The run is traced with the torch profiler; the report lists which files the hot-path modules
 were imported from, the CUDA kernels launched and the ATen ops called.
@@ -41,6 +44,18 @@ def main():
     def init_without_verbose(self, *a, verbose=None, **kw):
         orig_init(self, *a, **kw)
     sched.__init__ = init_without_verbose
+
+    orig_getitem = torch.Tensor.__getitem__
+
+    def getitem_with_device_fix(self, idx):
+        try:
+            return orig_getitem(self, idx)
+        except RuntimeError as exc:
+            if "indices should be either on cpu" not in str(exc):
+                raise
+            fix = lambda i: i.to(self.device) if isinstance(i, torch.Tensor) else i   # noqa: E731
+            return orig_getitem(self, tuple(fix(i) for i in idx) if isinstance(idx, tuple) else fix(idx))
+    torch.Tensor.__getitem__ = getitem_with_device_fix
 
     sys.argv = [script] + argv
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:

@@ -325,6 +325,54 @@ def test_step_update_adjoint(pk, case):
         assert_parity(gours[1].cpu(), gref[1], 2e-5, "update grad_mu")
 
 
+@pytest.mark.parametrize("case", ["burgers_p", "rd_p", "burgers_f", "rd_f"])
+def test_adjoint_at_the_reference_mesh_against_oracle_autograd(pk, case):
+    """The compile-time-period adjoint kernel (257 -> 33 / 49, coarse_adjoint_periodic.cuh) against
+    torch.autograd over the oracle's train2D.py:66-79,235-238 at FULL size, B = 3, mixed sign:
+    grad_u, grad_mu, grad_nn; with and without the identity term; from the saved coarse state
+    (what autograd uses) and from u (the plain C entries), which must agree bit for bit."""
+    import ctypes as C
+    L = pk["lib"]
+    lib = L.load()
+    g = load_golden("step_257.npz")
+    c = CASES[case]
+    gen = torch.Generator().manual_seed(31)
+    u, nn = g["u"], g["nn"]
+    mu = torch.linspace(c["mu"] * 0.4, c["mu"], 3).reshape(-1, 1, 1, 1)
+    om, os_ = g["outmean"], g["outstd"]
+    cot = torch.randn(3, 2, 257, 257, generator=gen)
+    ostep = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    step = pk["CoarseStep"](257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
+    lv = [t.clone().requires_grad_(True) for t in (u, mu, nn)]
+    yref = O.ppnn_update(lv[0], ostep.pde_du(lv[0], lv[1]), lv[2], om, os_)
+    gref = torch.autograd.grad(yref, lv, cot, allow_unused=True)
+    lc = [t.cuda().requires_grad_(True) for t in (u, mu, nn)]
+    y = step.step_update(lc[0], lc[1], lc[2], om, os_)
+    gours = torch.autograd.grad(y, lc, cot.cuda(), allow_unused=True)
+    assert_parity(gours[0].cpu(), gref[0], TOL, case + " update grad_u")
+    assert_parity(gours[2].cpu(), gref[2], TOL, case + " update grad_nn")
+    if gref[1] is not None and gref[1].abs().max() > 0:
+        assert_parity(gours[1].cpu(), gref[1], 2e-5, case + " update grad_mu")
+    # pde_du alone (no identity term)
+    ur = u.clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad(ostep.pde_du(ur, mu), ur, cot)
+    uc = u.cuda().requires_grad_(True)
+    (gc,) = torch.autograd.grad(step.pde_du(uc, mu.cuda()), uc, cot.cuda())
+    assert_parity(gc.cpu(), gr, TOL, case + " pde_du grad_u")
+    # plain entry (re-gathers the coarse state from u) == saved-state entry, bit for bit
+    ud, md, cd = u.cuda(), mu.reshape(-1).cuda().contiguous(), cot.cuda()
+    gu1, gm1, gn1 = torch.empty_like(ud), torch.empty(3, device="cuda"), torch.empty(3, 2, 256, 256, device="cuda")
+    L.check(lib.ppnn_step_update_bwd(C.byref(step.cfg), ud.data_ptr(), md.data_ptr(), cd.data_ptr(), L.f2(os_),
+                                     gu1.data_ptr(), gm1.data_ptr(), gn1.data_ptr(), 3, L.stream()), "bwd")
+    assert torch.equal(gu1, gours[0]) and torch.equal(gn1, gours[2])
+    assert torch.equal(gm1.reshape(-1), gours[1].reshape(-1))
+    # run to run determinism (the scatter-adds of phase 4 hit disjoint points on these meshes)
+    gu2 = torch.empty_like(ud)
+    L.check(lib.ppnn_pde_du_bwd(C.byref(step.cfg), ud.data_ptr(), md.data_ptr(), cd.data_ptr(), gu2.data_ptr(), None,
+                                3, 1, L.stream()), "bwd")
+    assert torch.equal(gu2, gu1)
+
+
 @pytest.mark.parametrize("case", ["burgers_p", "rd_p"])
 def test_step_inputs(pk, case):
     gen = torch.Generator().manual_seed(22)

@@ -234,6 +234,115 @@ def workload_config(B, n):
     return c
 
 
+# ----------------------------------------------------------------------------- config 3 / config 4 legs
+def train_leg(torch, dist, dev, world, rank, local, timed, L):
+    """BASELINE configs[2]: one training step of cases/burgers_fPDE.yaml THROUGH the PDE-preserving step -- a
+    4-step unrolled rollout u <- padBC_rd(net(norm u, norm mu)*outstd + outmean) + u + pde_du(u, mu) with the
+    fused kernel forward and the adjoint kernel backward, a cnn2d-shaped network (ignores pdeu, models.py:95-96),
+    100 samples per GPU (= the YAML's batchsize 800 on 8 GPUs), Adam; with N > 1 the network is wrapped in
+    DistributedDataParallel: one NCCL all-reduce of its fp32 gradients per step over NVLink."""
+    import ctypes as C
+    from ppnn_b200 import CoarseStep
+    from ppnn_b200.nets import ConvResNet
+    Bt, unroll, F = 100, 4, 257
+    step = CoarseStep(F, 49, "burgers2DFu", "burgers2DFv", 0.02, 3.2)
+    torch.manual_seed(10)
+    net = ConvResNet(uses_pde=False).to(dev)
+    nparams = sum(p.numel() for p in net.parameters())
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    u0 = synth_fields(Bt, F, dev, 300 + rank)
+    target = synth_fields(Bt, F, dev, 400 + rank)
+    mu = torch.linspace(0.02, 0.07, 6, device=dev)[torch.arange(Bt, device=dev) % 6].reshape(Bt, 1, 1, 1)
+    mun = (mu - 0.045) / 0.017
+    inmean, instd = torch.zeros(1, 2, 1, 1, device=dev), torch.full((1, 2, 1, 1), 0.3, device=dev)
+    outmean, outstd = [0.0, 0.0], [1e-2, 1e-2]
+    losses = []
+
+    def train_step(m):
+        u = u0
+        for _ in range(unroll):
+            nn_out = m((u[:, :, :-1, :-1] - inmean) / instd, mun)
+            u = step.step_update(u, mu, nn_out, outmean, outstd)
+        loss = torch.nn.functional.mse_loss(u, target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+
+    t_full = timed(lambda: train_step(model), 5, 2)
+    out = {"ms_per_train_step": t_full, "unroll": unroll, "batch_per_gpu": Bt, "global_batch": Bt * world,
+           "traj_steps_per_s": world * Bt * unroll / (t_full * 1e-3), "params": nparams,
+           "allreduce_bytes": 4 * nparams if world > 1 else 0,
+           "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+    if world > 1:
+        def local_step():
+            with model.no_sync():                                # same step, gradients NOT all-reduced
+                train_step(model)
+        t_local = timed(local_step, 5, 2)
+        out["ms_without_allreduce"] = t_local
+        out["allreduce_exposed_ms"] = t_full - t_local
+    # the PDE-preserving part alone: `unroll` x (update kernel saving the coarse state + its one-launch backward)
+    lib = L.load()
+    muv = mu.reshape(-1).contiguous()
+    nn = torch.randn(Bt, 2, F - 1, F - 1, device=dev)
+    o, gu, gnn = torch.empty_like(u0), torch.empty_like(u0), torch.empty_like(nn)
+    gmu = torch.empty(Bt, device=dev)
+    coarse = torch.empty(Bt, 2, 48, 48, device=dev)
+    om, os_ = L.f2(outmean), L.f2(outstd)
+
+    def pde_part():
+        for _ in range(unroll):
+            L.check(lib.ppnn_step_update_save(C.byref(step.cfg), u0.data_ptr(), muv.data_ptr(), nn.data_ptr(), om, os_,
+                                              o.data_ptr(), coarse.data_ptr(), Bt, L.stream()), "update")
+            L.check(lib.ppnn_step_update_bwd_saved(C.byref(step.cfg), coarse.data_ptr(), muv.data_ptr(), target.data_ptr(), os_,
+                                                   gu.data_ptr(), gmu.data_ptr(), gnn.data_ptr(), Bt, L.stream()), "bwd")
+    t_pde = timed(pde_part, 5, 2)
+
+    def net_part():
+        for _ in range(unroll):
+            y = net((u0[:, :, :-1, :-1] - inmean) / instd, mun)
+            y.backward(nn)
+        net.zero_grad(set_to_none=True)
+    t_net = timed(net_part, 3, 1)
+    out.update(ms_pde_kernels=t_pde, ms_network_fwd_bwd=t_net,
+               share_pde_kernels=t_pde / t_full, share_network=t_net / t_full,
+               limited_by="the PyTorch network (cuDNN fp32/TF32 convolutions + LayerNorm), which north_star leaves in "
+                          "PyTorch; the fused step + adjoint are a few per cent of the step and the all-reduce overlaps "
+                          "with the backward pass",
+               note="CUDA events, max over ranks; 2 warm-up + 5 timed train steps; synthetic periodic fields")
+    return out
+
+
+def datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier):
+    """BASELINE configs[3]: the fine-grid Burgers generator (operators.py:403-492) at the reference's LENGTH
+    (20 001 steps, snapshot every 200 => 101 snapshots), 1025^2 (the reference's duplicated-endpoint convention at
+    config 4's resolution), 8 viscosities x 8 initial conditions = 64 samples PER GPU, sharded with no communication.
+    End to end including set-up (initial conditions, buffers, graph capture): wall clock, max over ranks."""
+    from ppnn_b200.datagen import generate
+    out = {}
+    for tag, kw in (("device_sink", dict(on_device=True)), ("host_sink_discard", dict(keep=False))):
+        barrier()
+        t0 = time.perf_counter()
+        tm = {}
+        data = generate(mesh=1025, para=8, repeat=8 * world, steps=20001, every=200, device=dev, rank=rank,
+                        world_size=world, timings=tm, **kw)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        finite = bool(torch.isfinite(data[:, -1]).all()) if data.numel() else None
+        del data
+        P = 64 * world
+        out[tag] = {"seconds": sec, "samples_per_s": P / sec, "setup_seconds": max_over_ranks(tm["setup_seconds"]),
+                    "solve_seconds": max_over_ranks(tm["solve_seconds"]),
+                    "gpoint_updates_per_s": P * 2 * 1025 * 1025 * 20001 / sec / 1e9,
+                    "snapshot_gb_per_gpu": 101 * 64 * 2 * 1025 * 1025 * 4 / 1e9, "finite": finite}
+        torch.cuda.empty_cache()
+    out["note"] = ("device_sink: the 101 snapshots stay in HBM (54 GB per GPU; the form PdeDataset trains from); "
+                   "host_sink_discard: every snapshot is copied to pinned host memory on a side stream and dropped "
+                   "(the box cannot hold 8 x 54 GB): solver + the D2H the reference does at operators.py:479-482")
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -247,6 +356,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from ppnn_b200.dist import bind_to_gpu_numa
+    numa_cores = bind_to_gpu_numa(local)              # pinned staging buffers next to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.load()
@@ -309,8 +420,38 @@ def run_ours(args):
                   "samples": len(idx), "sample_indices": idx, "against": pkind, "tolerance": 1e-5}
         parity["ok"] = bool(parity["rel_l2"] <= 1e-5 and parity["rel_max"] <= 1e-5)
 
+    # ---- host link ceiling: plain pinned-memory copies, every rank at once (one cudaMemcpyAsync per call) ----
+    def link_ceiling():
+        n = 64 << 20                                        # 256 MB per copy
+        h_in = torch.empty(n, dtype=torch.float32, pin_memory=True).fill_(1.0)
+        h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        d_in, d_out = torch.empty(n, device=dev), torch.ones(n, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        reps, nbytes = 6, n * 4
+
+        def run(h2d, d2h):
+            cur = torch.cuda.current_stream()
+            s1.wait_stream(cur); s2.wait_stream(cur)
+            for _ in range(reps):
+                if h2d:
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(h_in, non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+            cur.wait_stream(s1); cur.wait_stream(s2)
+        res = {}
+        for tag, h2d, d2h in (("h2d", True, False), ("d2h", False, True), ("bidir", True, True)):
+            t = timed(lambda: run(h2d, d2h), 2, 1)          # ms per run of `reps` copies each way, max over ranks
+            res[tag + "_gbs_per_gpu"] = reps * nbytes / t / 1e6
+        res["aggregate_bidir_gbs"] = world * 2 * res["bidir_gbs_per_gpu"]
+        res["how"] = ("256 MB pinned<->device copies, 6 back to back per direction, all ranks at once, CUDA events, max over "
+                      "ranks; bidir = H2D and D2H streams together, per-direction rate")
+        return res
+    link = link_ceiling()
+
     # ---- e2e: pinned host buffers -> HostStepPipeline (H2D / kernel / D2H on three streams) ----
-    nchunk = 8
+    nchunk = 16
     u_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True).copy_(u)
     nn_h = torch.empty(nn.shape, dtype=torch.float32, pin_memory=True).copy_(nn)
     out_h = torch.empty(u.shape, dtype=torch.float32, pin_memory=True)
@@ -327,6 +468,9 @@ def run_ours(args):
     e2e_ok = bool(torch.equal(out_h, out.cpu()))             # the WHOLE batch: every chunk incl. the ragged last one
     h2d = (u.numel() + nn.numel()) * 4
     d2h = u.numel() * 4
+    # the step cannot beat either direction at its own measured rate, nor the sum at the both-directions-busy rate
+    e2e_floor_ms = max(h2d / link["h2d_gbs_per_gpu"], d2h / link["d2h_gbs_per_gpu"],
+                       (h2d + d2h) / (2 * link["bidir_gbs_per_gpu"])) / 1e6
 
     # ---- secondary kernels (same case), device resident ------------------------------
     extras = {}
@@ -401,6 +545,27 @@ def run_ours(args):
         extras["fine_burgers_step_intended_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
                                                         "hbm_gbs": 8 * fpts / t / 1e6}
 
+        del fu, a, b_, a2, b2
+        n = 1024                                     # BASELINE config 4 as named: 1024^2 true periodic
+        fu = synth_fields(bf, n, dev, 98)
+        a, b_ = fu[:, 0].contiguous(), fu[:, 1].contiguous()
+        a2, b2 = torch.empty_like(a), torch.empty_like(b_)
+        fbp = FineBurgers(endpoint=False)
+        fpts = bf * 2 * n * n
+        t = timed(lambda: fbp.step_(a, b_, mf, a2, b2), reps * 2, 3)
+        extras["fine_burgers_step_1024x64_true_periodic"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
+                                                             "hbm_gbs": 8 * fpts / t / 1e6}
+        del fu, a, b_, a2, b2
+
+        try:
+            extras["train_unrolled_burgers_fPDE"] = train_leg(torch, dist, dev, world, rank, local, timed, L)
+        except Exception as exc:
+            extras["train_unrolled_error"] = repr(exc)[:300]
+        try:
+            extras["datagen_1025x64_per_gpu"] = datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier)
+        except Exception as exc:
+            extras["datagen_error"] = repr(exc)[:300]
+
         # rollout (train2D.py:230-245): K1 -> network -> K2 per step, CUDA-graph replayed,
         # around a random-weight network with the layer shapes of cnn2dRich (ppnn_b200/nets.py)
         try:
@@ -462,8 +627,10 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e, "steps": e2e_steps, "matches_resident_result": e2e_ok,
+                    "link_ceiling": link, "link_floor_ms_per_step": e2e_floor_ms,
+                    "frac_of_link_ceiling": e2e_floor_ms / ms_e2e, "numa_bound_cores": len(numa_cores) if numa_cores else None,
                     "api": "ppnn_b200.HostStepPipeline.run -> CoarseStep.step_update_ -> ppnn_step_update (C ABI), pinned "
-                           "host buffers, 8 chunks through separate H2D / kernel / D2H streams (ring of 3 device buffer sets)"},
+                           "host buffers, 16 chunks through separate H2D / kernel / D2H streams (ring of 3 device buffer sets)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": "static: ncu --set full capture of this kernel at this shape "

@@ -29,6 +29,33 @@ def world() -> Tuple[int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), so that
+    pinned host buffers allocated afterwards are first-touched next to the GPU's PCIe root and the host-side
+    copies of the staging pipelines do not cross the socket interconnect.  Returns the core list, or None when
+    NVML or the affinity call is unavailable (nothing changes then).  Call before allocating pinned memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous, balanced shard ``[lo, hi)`` of ``n`` samples for ``rank``: the first
     ``n % world_size`` ranks own one extra sample, the union over ranks is ``[0, n)``."""

@@ -103,7 +103,7 @@ int ppnn_resample_fwd(const float* in, float* out, long planes, int Hin, int Win
 int ppnn_resample_fwd_strided(const float* in, float* out, long planes, long in_plane_stride,
                               int Hin, int Win, int Hout, int Wout, int mode, int align_corners,
                               void* stream);
-/* adjoint w.r.t. `in`; grad_in [planes,Hin,Win] is zero-filled then accumulated. */
+/* adjoint w.r.t. `in`; grad_in [planes,Hin,Win] is fully overwritten (gather: deterministic). */
 int ppnn_resample_bwd(const float* grad_out, float* grad_in, long planes, int Hin, int Win,
                       int Hout, int Wout, int mode, int align_corners, void* stream);
 
@@ -215,6 +215,15 @@ int ppnn_fine_burgers_step(const float* u, const float* v, const float* mu,
                            float* u_out, float* v_out, int B, int H, int W,
                            int endpoint, int mode, int adv_accuracy, int diff_accuracy,
                            float dt, float dx, float dy, void* stream);
+
+/* Random-Fourier initial condition of the generator (src/operators.py:423-445): for every sample
+ * out[b,i,j] = sum_{k,l=-modes..modes} a_kl sin(k x_i + l y_j) + c_kl cos(k x_i + l y_j) on
+ * x = y = linspace(0, 2*pi, n), min-max normalised per sample to [offset, offset + 1] (the reference:
+ * modes = 4, offset = 0.1).  coef [B, (2*modes+1)^2, 2] holds (a, c) in the reference's (k, l) loop order
+ * (the values its torch.randn_like calls draw); out [B, n, n]; minmax_scratch [B, 2] floats of device
+ * scratch (the library does not allocate).  modes <= 8.                                              */
+int ppnn_fourier_ic(const float* coef, float* out, float* minmax_scratch,
+                    int B, int n, int modes, float offset, void* stream);
 
 /* Generic fused explicit step  f <- f + dt*rhs(f)  for any rhs id pair on a
  * periodic fine grid (the commented generators of operators.py:494-748: RD,

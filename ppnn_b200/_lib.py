@@ -63,6 +63,7 @@ _SIGNATURES = {
     "ppnn_dataset_emit": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_long, C.c_long,
                                     C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P]),
     "ppnn_fine_burgers_step": (C.c_int, [_P] * 5 + [C.c_int] * 7 + [C.c_float] * 3 + [_P]),
+    "ppnn_fourier_ic": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "ppnn_fine_rhs_step": (C.c_int, [_P] * 5 + [C.c_int] * 8 + [C.c_float] * 3 + [_P]),
 }
 EXPORTS = tuple(_SIGNATURES)

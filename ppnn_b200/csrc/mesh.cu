@@ -3,8 +3,9 @@
 // semantics -- source index = scale * o (align_corners) or scale*(o+.5)-.5,
 // bilinear weights (1-t, t) with the +1 neighbour dropped at the border, Keys
 // cubic A = -0.75 with taps clamped to the border.  Forward is
-// a gather (thread per output, coalesced stores); the adjoint scatters with
-// atomics into a zero-filled grad_in, as torch's own CUDA backward does.
+// a gather (thread per output, coalesced stores); the adjoint is a gather too
+// (thread per grad_in element, fixed summation order): unlike torch's own CUDA
+// backward, which scatters with atomics, it is bit-identical from run to run.
 #include "common.cuh"
 
 namespace ppnn {
@@ -18,7 +19,7 @@ struct ResampleParams {
     long total;     // planes * Hout * Wout
 };
 
-template <int MODE, bool BWD>
+template <int MODE>
 __global__ void __launch_bounds__(256)
 resample_kernel(const ResampleParams p) {
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
@@ -27,27 +28,18 @@ resample_kernel(const ResampleParams p) {
         long t = idx / p.Wout;
         int i = (int)(t % p.Hout);
         long pl = t / p.Hout;
-        size_t base = BWD ? (size_t)pl * p.Hin * p.Win : (size_t)pl * p.in_stride;
-        float g = BWD ? __ldg(p.in + idx) : 0.f;        // BWD: `in` is grad_out, `out` is grad_in
+        const float* q = p.in + (size_t)pl * p.in_stride;
         if (MODE == PPNN_BILINEAR) {
             float si = resample_src(p.sh, i, p.align, false), sj = resample_src(p.sw, j, p.align, false);
             int i0 = min((int)si, p.Hin - 1), j0 = min((int)sj, p.Win - 1);
             int di = i0 < p.Hin - 1 ? 1 : 0, dj = j0 < p.Win - 1 ? 1 : 0;
             float li = si - (float)i0, lj = sj - (float)j0;
             float h0 = 1.f - li, w0 = 1.f - lj;
-            size_t o00 = base + (size_t)i0 * p.Win + j0;
+            size_t o00 = (size_t)i0 * p.Win + j0;
             size_t o01 = o00 + dj, o10 = o00 + (size_t)di * p.Win, o11 = o10 + dj;
-            if (!BWD) {
-                const float* q = p.in;
-                float v = h0 * (w0 * __ldg(q + o00) + lj * __ldg(q + o01)) +
-                          li * (w0 * __ldg(q + o10) + lj * __ldg(q + o11));
-                st_stream(p.out + idx, v);
-            } else {
-                atomicAdd(p.out + o00, h0 * w0 * g);
-                atomicAdd(p.out + o01, h0 * lj * g);
-                atomicAdd(p.out + o10, li * w0 * g);
-                atomicAdd(p.out + o11, li * lj * g);
-            }
+            float v = h0 * (w0 * __ldg(q + o00) + lj * __ldg(q + o01)) +
+                      li * (w0 * __ldg(q + o10) + lj * __ldg(q + o11));
+            st_stream(p.out + idx, v);
         } else {
             float si = resample_src(p.sh, i, p.align, true), sj = resample_src(p.sw, j, p.align, true);
             float fi = floorf(si), fj = floorf(sj);
@@ -61,20 +53,85 @@ resample_kernel(const ResampleParams p) {
             float v = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                size_t row = base + (size_t)clampi(i0 - 1 + a, 0, p.Hin - 1) * p.Win;
-                if (!BWD) {
-                    const float* q = p.in + row;
-                    // W pass then H pass, like torch's cubic_interp1d nesting
-                    float r = __ldg(q + cj[0]) * wj[0] + __ldg(q + cj[1]) * wj[1] +
-                              __ldg(q + cj[2]) * wj[2] + __ldg(q + cj[3]) * wj[3];
-                    v += r * wi[a];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) atomicAdd(p.out + row + cj[k], wi[a] * wj[k] * g);
-                }
+                const float* r = q + (size_t)clampi(i0 - 1 + a, 0, p.Hin - 1) * p.Win;
+                // W pass then H pass, like torch's cubic_interp1d nesting
+                v += (__ldg(r + cj[0]) * wj[0] + __ldg(r + cj[1]) * wj[1] +
+                      __ldg(r + cj[2]) * wj[2] + __ldg(r + cj[3]) * wj[3]) * wi[a];
             }
-            if (!BWD) st_stream(p.out + idx, v);
+            st_stream(p.out + idx, v);
         }
+    }
+}
+
+// ---- adjoint as a GATHER: thread = one element of grad_in, sums the contributions of every output whose
+// window reaches it in a fixed (row-major) order => bit-identical from run to run (no atomics, no zero fill).
+// weight with which output index o feeds input index I along one axis (0 if it does not)
+template <int MODE>
+__device__ __forceinline__ float adjoint_weight(float scale, bool align, int o, int I, int nin) {
+    if (MODE == PPNN_BILINEAR) {
+        const float s = resample_src(scale, o, align, false);
+        const int i0 = min((int)s, nin - 1);
+        const int d = i0 < nin - 1 ? 1 : 0;
+        const float l = s - (float)i0;
+        float w = 0.f;
+        if (i0 == I) w += 1.f - l;
+        if (i0 + d == I) w += l;
+        return w;
+    }
+    const float s = resample_src(scale, o, align, true);
+    const float fl = floorf(s);
+    const int i0 = (int)fl;
+    float wv[4];
+    cubic_weights(s - fl, wv);
+    float w = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        if (clampi(i0 - 1 + a, 0, nin - 1) == I) w += wv[a];
+    return w;
+}
+
+// conservative range of output indices whose window can reach input index I (exact test: adjoint_weight)
+template <int MODE>
+__device__ __forceinline__ void adjoint_range(float scale, bool align, int I, int nin, int nout, int* lo, int* hi) {
+    const float reach = MODE == PPNN_BILINEAR ? 1.f : 2.f;
+    const float off = align ? 0.f : 0.5f;
+    int a = 0, b = nout - 1;
+    if (scale > 0.f) {
+        a = (int)floorf(((float)I - reach + off) / scale - off) - 1;
+        b = (int)ceilf(((float)I + reach + off) / scale - off) + 1;
+    }
+    if (I == 0) a = 0;                     // clamped taps below the first input pile up on it
+    if (I == nin - 1) b = nout - 1;        // ... and beyond the last one
+    *lo = max(a, 0);
+    *hi = min(b, nout - 1);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+resample_adjoint_kernel(const ResampleParams p, long total_in) {
+    // `in` is grad_out [planes, Hout, Wout], `out` is grad_in [planes, Hin, Win]
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_in;
+         idx += (long)gridDim.x * blockDim.x) {
+        const int J = (int)(idx % p.Win);
+        const long t = idx / p.Win;
+        const int I = (int)(t % p.Hin);
+        const long pl = t / p.Hin;
+        const float* g = p.in + (size_t)pl * p.Hout * p.Wout;
+        int ilo, ihi, jlo, jhi;
+        adjoint_range<MODE>(p.sh, p.align, I, p.Hin, p.Hout, &ilo, &ihi);
+        adjoint_range<MODE>(p.sw, p.align, J, p.Win, p.Wout, &jlo, &jhi);
+        float acc = 0.f;
+        for (int i = ilo; i <= ihi; ++i) {
+            const float wi = adjoint_weight<MODE>(p.sh, p.align, i, I, p.Hin);
+            if (wi == 0.f) continue;
+            float row = 0.f;
+            for (int j = jlo; j <= jhi; ++j) {
+                const float wj = adjoint_weight<MODE>(p.sw, p.align, j, J, p.Win);
+                if (wj != 0.f) row += wj * __ldg(g + (size_t)i * p.Wout + j);
+            }
+            acc += wi * row;
+        }
+        p.out[idx] = acc;
     }
 }
 
@@ -142,8 +199,12 @@ static int run_resample(const float* in, float* out, long planes, long in_stride
     p.total = planes * Hout * Wout;
     cudaStream_t s = (cudaStream_t)stream;
     if (bwd) {
-        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)planes * Hin * Win * sizeof(float), s);
-        if (e != cudaSuccess) return (int)e;
+        const long total_in = planes * Hin * Win;
+        long nb = (total_in + 255) / 256;
+        if (nb > 148L * 32) nb = 148L * 32;
+        if (mode == PPNN_BILINEAR) resample_adjoint_kernel<PPNN_BILINEAR><<<(unsigned)nb, 256, 0, s>>>(p, total_in);
+        else                       resample_adjoint_kernel<PPNN_BICUBIC><<<(unsigned)nb, 256, 0, s>>>(p, total_in);
+        return launch_status();
     }
     long blocks = (p.total + 255) / 256;
     if (blocks > 148L * 32) blocks = 148L * 32;
@@ -153,13 +214,8 @@ static int run_resample(const float* in, float* out, long planes, long in_stride
         bicubic_up_kernel<<<grid, 128, 0, s>>>(p);
         return launch_status();
     }
-    if (mode == PPNN_BILINEAR) {
-        if (bwd) resample_kernel<PPNN_BILINEAR, true><<<g, 256, 0, s>>>(p);
-        else     resample_kernel<PPNN_BILINEAR, false><<<g, 256, 0, s>>>(p);
-    } else {
-        if (bwd) resample_kernel<PPNN_BICUBIC, true><<<g, 256, 0, s>>>(p);
-        else     resample_kernel<PPNN_BICUBIC, false><<<g, 256, 0, s>>>(p);
-    }
+    if (mode == PPNN_BILINEAR) resample_kernel<PPNN_BILINEAR><<<g, 256, 0, s>>>(p);
+    else                       resample_kernel<PPNN_BICUBIC><<<g, 256, 0, s>>>(p);
     return launch_status();
 }
 

@@ -230,6 +230,30 @@ def test_mesh_converter_adjoint(pk):
         assert_parity(gours.cpu(), gref, TOL, f"mesh {fn} adjoint")
 
 
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("align", [True, False])
+def test_resample_adjoint_is_a_deterministic_gather(pk, mode, align):
+    """ppnn_resample_bwd against autograd over F.interpolate on the CPU for down- and up-sampling,
+    rectangular and non-integer ratios, both align_corners conventions; two runs bit-identical."""
+    import torch.nn.functional as Fn
+    L = pk["lib"]
+    lib = L.load()
+    gen = torch.Generator().manual_seed(13)
+    m = 0 if mode == "bilinear" else 1
+    for (hin, win, hout, wout) in ((33, 33, 9, 9), (13, 13, 65, 65), (21, 30, 40, 57), (40, 57, 9, 13), (1, 101, 1, 11), (7, 5, 7, 5)):
+        x = torch.randn(3, 1, hin, win, generator=gen, requires_grad=True)
+        y = Fn.interpolate(x, size=(hout, wout), mode=mode, align_corners=align)
+        cot = torch.randn(y.shape, generator=gen)
+        (gref,) = torch.autograd.grad(y, x, cot)
+        cd = cot.cuda().contiguous()
+        g1 = torch.full((3, 1, hin, win), float("nan"), device="cuda")
+        g2 = torch.full_like(g1, float("nan"))
+        for g in (g1, g2):
+            L.check(lib.ppnn_resample_bwd(cd.data_ptr(), g.data_ptr(), 3, hin, win, hout, wout, m, int(align), L.stream()), "bwd")
+        assert torch.equal(g1, g2)
+        assert_parity(g1.cpu(), gref, TOL, f"{mode} adjoint {hin}x{win}->{hout}x{wout} align={align}")
+
+
 # --------------------------------------------------------------------- Tier B
 CASES = {
     "burgers_p": dict(cmesh=33, rhsu="burgers2Dpu", rhsv="burgers2Dpv", dt=0.02, length=3.2, mu=0.07),
@@ -627,6 +651,25 @@ def test_datagen_sharding_snapshots_and_oracle(pk):
     _, _, su, sv = O.fine_burgers_run(u0, v0, mu, 13, every=4)
     ref = torch.stack((torch.cat(su, dim=1), torch.cat(sv, dim=1)), dim=2)
     assert_parity(one, ref, TOL, "datagen vs oracle")
+
+
+@pytest.mark.parametrize("n,b", [(257, 5), (65, 3), (1025, 2), (100, 4)])
+def test_fourier_initial_condition_against_the_oracle(pk, n, b):
+    """operators.py:423-445 (81 modes, per-sample min-max normalisation to [0.1, 1.1]): the separable
+    kernel against the oracle's term-by-term sum with the same coefficients; fp32, 1e-5."""
+    from ppnn_b200 import datagen, dist as D
+    coef = D.fourier_coefficients(10, 3, 3 + b)
+    for fld in range(2):
+        ours = datagen.fourier_initial_condition(coef[:, fld], n, "cuda")
+        ref = O.fourier_initial_condition(coef[:, fld], n)
+        assert ours.shape == ref.shape == (b, 1, n, n)
+        assert_parity(ours.cpu(), ref, TOL, f"IC n={n} field {fld}")
+        ref64 = O.fourier_initial_condition(coef[:, fld].double(), n)
+        assert_parity(ours.cpu().double(), ref64, TOL, f"IC n={n} field {fld} vs fp64")
+        lo, hi = ours.amin(dim=(1, 2, 3)), ours.amax(dim=(1, 2, 3))
+        assert torch.allclose(lo, torch.full_like(lo, 0.1), atol=1e-6) and torch.allclose(hi, torch.full_like(hi, 1.1), atol=1e-6)
+    # the duplicated endpoint is NOT bit-identical to its twin in the reference either: only nearly periodic
+    assert (ours[:, :, 0, :] - ours[:, :, -1, :]).abs().max() < 1e-4
 
 
 @pytest.mark.parametrize("n,endpoint", [(129, True), (1025, True), (512, False)])

@@ -277,11 +277,7 @@ using namespace ppnn;
 // the reference's own meshes: compile-time period of the prolongation (coarse_adjoint_periodic.cuh)
 template <int PER, int ADV>
 static int launch_adjoint_periodic(const CoarseParams& p, const AdjParams& a, int B, void* stream) {
-    PhaseWeights pw;
-    for (int r = 0; r < 16; ++r) {
-        const float s = p.suh * (float)(r < PER ? r : 0);
-        cubic_weights(s - floorf(s), pw.w[r]);
-    }
+    const PhaseWeights pw = make_phase_weights(p.suh, PER);
     void (*kern)(CoarseParams, AdjParams, PhaseWeights, const float*);
     kern = a.gnn ? coarse_adjoint_periodic_kernel<PER, ADV, true, true>
          : a.add_identity ? coarse_adjoint_periodic_kernel<PER, ADV, true, false>

@@ -28,8 +28,6 @@
 
 namespace ppnn {
 
-struct PhaseWeights { float w[16][4]; };     // Keys-cubic weights of the (up to 16) phases of one period
-
 __device__ __forceinline__ void st_keep(float* p, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }

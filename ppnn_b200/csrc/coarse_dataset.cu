@@ -36,9 +36,10 @@ struct DatasetIO {
     const float* x_end;
 };
 
-template <int FWC, bool EMIT>
+// PER > 0: compile-time prolongation period for the reference's meshes (see coarse_step_staged.cuh)
+template <int FWC, bool EMIT, int PER = 0, int ADV = 0>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
-dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl, const StagedLayout lay) {
+dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl, const StagedLayout lay, const PhaseWeights pw) {
     extern __shared__ float4 smem4[];
     float4* roww = smem4;
     int* rowi = reinterpret_cast<int*>(roww + p.FH);
@@ -129,7 +130,7 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
         gather_coarse<true>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
-        build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
+        if (PER == 0) build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
 
@@ -189,7 +190,95 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
     }
 
     // ---- phase 3b: warp = (row group, 32-column chunk), operands from the ring ----
-    if (warp < nconsumers) {
+    if constexpr (PER > 0) {
+        constexpr int R = kStageRows, NACC = ADV + 3, SPLIT = 128;
+        static_assert(SPLIT % PER == 0 && PER % R == 0 && FWC == 257 && PPNN_STEP_WARPS == 16, "period layout");
+        const int g = warp >> 3;
+        const int rs = g ? SPLIT : 0;
+        const int j = (warp & 7) * 32 + lane;                   // 0 .. 255
+        float wy[4]; int j0;
+        cubic_entry(p.suw, j, &j0, wy);
+        const float* rc0 = rf + ext_index(j0 - 1, p.CW);
+        const float* rc1 = rf + ext_index(j0, p.CW);
+        const float* rc2 = rf + ext_index(j0 + 1, p.CW);
+        const float* rc3 = rf + ext_index(j0 + 2, p.CW);
+        auto yrow = [&](int I) -> float {
+            const int o = ext_index(I, p.CH) * p.NW;
+            return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
+        };
+        const float m0 = f ? io.m[0][1] : io.m[0][0], s0 = f ? io.s[0][1] : io.s[0][0];
+        const float m1 = f ? io.m[1][1] : io.m[1][0], s1 = f ? io.s[1][1] : io.s[1][0];
+        const float m2 = f ? io.m[2][1] : io.m[2][0], s2 = f ? io.s[2][1] : io.s[2][0];
+        const float rs0 = 1.f / s0, rs1 = 1.f / s1, rs2 = 1.f / s2;
+        const size_t o0 = ((size_t)b * 2 + f) * nplane + (size_t)rs * PW + j;
+        const int lead_u = (int)(reinterpret_cast<uintptr_t>(uf) & 15) >> 2;
+        const int lead_x = (int)(reinterpret_cast<uintptr_t>(xf) & 15) >> 2;
+        const float* su_base = sU + (size_t)g * lay.ustage + lead_u + j;
+        const float* sx_base = sX + (size_t)g * lay.ustage + lead_x + j;
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const size_t ustep = (size_t)2 * lay.ustage;
+        auto stream_rows = [&](auto dupl_tag) {
+            constexpr bool DUPL = decltype(dupl_tag)::value;
+            const bool dupl = DUPL && lane == 0;                // this lane counts the duplicated endpoint column too
+            float* unp = EMIT ? io.u_norm + o0 : nullptr;
+            float* pnp = EMIT ? io.p_norm + o0 : nullptr;
+            float* lnp = EMIT ? io.l_norm + o0 : nullptr;
+            const float* su = su_base;
+            const float* sx = sx_base;
+            int s = 0; uint32_t ph = 0;
+            int base = g ? SPLIT * ADV / PER : 0;
+            float h[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) h[k] = yrow(base - 1 + k);
+            auto emit = [&](int q, float pde, bool last_row) {
+                if (EMIT) {
+                    if (!last_row) {
+                        const float uu = su[q * FW];
+                        const float lab = (sx[q * FW] - uu) - pde;    // (u_{t+1} - u_t) - pdeu, in the reference's order
+                        st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
+                        st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
+                        st_stream(lnp + (size_t)q * PW, div_by(lab - m2, s2, rs2));
+                    }
+                } else {
+                    a_p += pde; a_pp += pde * pde;
+                    if (DUPL && dupl) { a_p += pde; a_pp += pde * pde; }
+                    if (!last_row) {
+                        const float uu = su[q * FW];
+                        const float lab = (sx[q * FW] - uu) - pde;
+                        a_u += uu; a_uu += uu * uu; a_l += lab; a_ll += lab * lab;
+                    }
+                }
+            };
+            auto advance = [&]() {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
+                if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
+                else { su += ustep; sx += ustep; }
+                if (EMIT) { unp += (size_t)R * PW; pnp += (size_t)R * PW; lnp += (size_t)R * PW; }
+            };
+            for (int per = 0; per < SPLIT / PER; ++per) {
+#pragma unroll
+                for (int bnd = 0; bnd < PER / R; ++bnd) {
+                    mbar_wait_addr(full_a + 8u * s, ph);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int r = bnd * R + q;
+                        const int o = (r * ADV) / PER;
+                        emit(q, h[o] * pw.w[r][0] + h[o + 1] * pw.w[r][1] + h[o + 2] * pw.w[r][2] + h[o + 3] * pw.w[r][3], false);
+                    }
+                    advance();
+                }
+                base += ADV;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) h[k] = k + ADV < NACC ? h[k + ADV] : yrow(base - 1 + k);
+            }
+            if (g == 1) {                                       // row 256: on the last coarse node, outside the cropped arrays
+                mbar_wait_addr(full_a + 8u * s, ph);
+                emit(0, h[1], true);
+            }
+        };
+        if ((warp & 7) == 0) stream_rows(std::true_type{}); else stream_rows(std::false_type{});
+    } else if (warp < nconsumers) {
         const int g = warp / pl.nchunk;
         const int chunk = warp - g * pl.nchunk;
         const int rs = g ? lay.split : 0, re = g ? p.FH : lay.split;
@@ -328,12 +417,18 @@ static int run_dataset(const ppnn_coarse_cfg* cfg, DatasetIO io, long B, bool em
     const size_t last = (size_t)(io.T > 0 ? (B - 1) + (B - 1) / io.T : B - 1);
     io.u_end = io.u + (last + 1) * plane2;
     io.x_end = io.x + (last + 1) * plane2;
-    void (*kern)(CoarseParams, DatasetIO, StepPlan, StagedLayout);
-    if (p.FW == 257) kern = emit ? dataset_pass_kernel<257, true> : dataset_pass_kernel<257, false>;
-    else             kern = emit ? dataset_pass_kernel<0, true> : dataset_pass_kernel<0, false>;
+    void (*kern)(CoarseParams, DatasetIO, StepPlan, StagedLayout, PhaseWeights);
+    const bool square = p.FH == 257 && p.FW == 257 && p.CH == p.CW && lay.split == 128 && pl.nchunk == 8 &&
+                        !PPNN_ENV_OFF("PPNN_NO_PERIODIC");
+    int per = 0;
+    if (square && p.CH == 49)      { per = 16; kern = emit ? dataset_pass_kernel<257, true, 16, 3> : dataset_pass_kernel<257, false, 16, 3>; }
+    else if (square && p.CH == 33) { per = 8;  kern = emit ? dataset_pass_kernel<257, true, 8, 1> : dataset_pass_kernel<257, false, 8, 1>; }
+    else if (p.FW == 257) kern = emit ? dataset_pass_kernel<257, true> : dataset_pass_kernel<257, false>;
+    else                  kern = emit ? dataset_pass_kernel<0, true> : dataset_pass_kernel<0, false>;
+    const PhaseWeights pw = make_phase_weights(p.suh, per);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)(2 * B), kStagedThreads, smem, (cudaStream_t)stream>>>(p, io, pl, lay);
+    kern<<<(unsigned)(2 * B), kStagedThreads, smem, (cudaStream_t)stream>>>(p, io, pl, lay, pw);
     return launch_status();
 }
 

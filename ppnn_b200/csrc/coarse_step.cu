@@ -329,12 +329,27 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
         if (smem2 <= 200 * 1024) {
             const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
             const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
-            void (*kern)(CoarseParams, StepIO, StepPlan, StagedLayout, const float*);
-            if (p.FW == 257) kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true> : coarse_step_staged_kernel<MODE, 257, false>;
-            else             kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
+            void (*kern)(CoarseParams, StepIO, StepPlan, StagedLayout, const float*, PhaseWeights);
+            // the reference's own meshes: prolongation period unrolled at compile time (16 fine rows per 3 coarse
+            // rows for 257 -> 49, 8 per 1 for 257 -> 33)
+            const bool square = p.FH == 257 && p.FW == 257 && p.CH == p.CW && lay.split == 128 && pl.nchunk == 8 &&
+                                !PPNN_ENV_OFF("PPNN_NO_PERIODIC");
+            int per = 0;
+            if (square && p.CH == 49) {
+                per = 16;
+                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 16, 3> : coarse_step_staged_kernel<MODE, 257, false, 16, 3>;
+            } else if (square && p.CH == 33) {
+                per = 8;
+                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 8, 1> : coarse_step_staged_kernel<MODE, 257, false, 8, 1>;
+            } else if (p.FW == 257) {
+                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true> : coarse_step_staged_kernel<MODE, 257, false>;
+            } else {
+                kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
+            }
+            const PhaseWeights pw = make_phase_weights(p.suh, per);
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;
-            kern<<<2 * B, kStagedThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end);
+            kern<<<2 * B, kStagedThreads, smem2, (cudaStream_t)stream>>>(p, io, pl, lay, u_end, pw);
             return launch_status();
         }
     }

@@ -17,6 +17,7 @@
 // tensor is clamped to its 16-byte-aligned end and the few trailing floats are
 // fetched with ordinary loads, so nothing outside the tensor is ever read.
 #pragma once
+#include <type_traits>
 #include "coarse_step_types.cuh"
 #include "tma.cuh"
 
@@ -150,10 +151,16 @@ constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 pro
 // One CTA = one (sample, field) plane.  Consumer warp = (row group g, 32-column
 // chunk): group 0 walks rows [0, split), group 1 rows [split, FH), both fed by
 // the same ring step.  HAS_NN: the update adds the network output (MODE_UPDATE).
-template <int MODE, int FWC, bool HAS_NN>
+//
+// PER > 0: the reference's own meshes (257 fine points, 33 / 49 coarse points), where the prolongation is
+// periodic in the fine row index -- every PER rows the 4-row window of W-interpolated coarse rows moves on
+// by exactly ADV rows and the PER weight phases repeat.  The consumer loop is then unrolled over one period:
+// which window entries a row uses, and when new ones are computed, is decided at compile time, and the
+// weights (`pw`, a kernel parameter) are constant-bank operands.  PER == 0: any mesh, run-time tables.
+template <int MODE, int FWC, bool HAS_NN, int PER = 0, int ADV = 0>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
-                          const float* u_end) {
+                          const float* u_end, const PhaseWeights pw) {
     // Index splits in the per-coarse-point phases go through small_div (fp32 reciprocal) except in the memory-bound
     // update with the network operand: there the shorter sequence changes ptxas' allocation under the 56-register
     // cap (12 bytes of spills in the band loop, 0.485 -> 0.494 ms) while the issue-bound modes gain 2-10 %.
@@ -234,7 +241,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         const bool both = (rid & PPNN_RHS_ADV) || (rid & ~3);
         const int lo = both ? 0 : f * nn2, hi = both ? 2 * nn2 : (f + 1) * nn2;
         gather_coarse<true, FASTDIV>(p, ub, plane, FW, lo, hi, cu, tid, kStepThreads);
-        build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
+        if (PER == 0) build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
 
@@ -310,6 +317,101 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     }
 
     // ---- phase 3b: warp = (row group, 32-column chunk), operands from the ring ----
+    if constexpr (PER > 0) {
+        // compile-time period: FH = FW = 257, two row groups [0,128) | [128,257), eight 32-column chunks each
+        constexpr int R = kStageRows, NACC = ADV + 3, SPLIT = 128;
+        static_assert(SPLIT % PER == 0 && PER % R == 0 && FWC == 257 && PPNN_STEP_WARPS == 16, "period layout");
+        const int g = warp >> 3;
+        const int rs = g ? SPLIT : 0;
+        const int j = (warp & 7) * 32 + lane;                   // 0 .. 255: every lane owns a column
+        float wy[4]; int j0;
+        cubic_entry(p.suw, j, &j0, wy);
+        const float* rc0 = rf + ext_index(j0 - 1, p.CW);
+        const float* rc1 = rf + ext_index(j0, p.CW);
+        const float* rc2 = rf + ext_index(j0 + 1, p.CW);
+        const float* rc3 = rf + ext_index(j0 + 2, p.CW);
+        auto yrow = [&](int I) -> float {                       // W pass of row I of the extended increment
+            const int o = ext_index(I, p.CH) * p.NW;
+            return rc0[o] * wy[0] + rc1[o] * wy[1] + rc2[o] * wy[2] + rc3[o] * wy[3];
+        };
+        const float rs0 = 1.f / s0, rs1 = 1.f / s1;
+        const int lead = (int)(reinterpret_cast<uintptr_t>(uf) & 15) >> 2;
+        const float* su_base = sU + (size_t)g * lay.ustage + lead + j;
+        const float* sn_base = sN + (size_t)g * lay.nstage + j;
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const size_t ustep = (size_t)2 * lay.ustage, nstep = (size_t)2 * lay.nstage;
+        // chunk 0 also owns the duplicated endpoint column (its increment is bit-identical to column 0's, see above):
+        // a separate instantiation of the loop, so the other seven chunks carry no instructions for it
+        auto stream_rows = [&](auto dupl_tag) {
+            constexpr bool DUPL = decltype(dupl_tag)::value;
+            const bool dupl = DUPL && lane == 0;
+            float* op = io.out ? io.out + ((size_t)b * 2 + f) * plane + (size_t)rs * FW + j : nullptr;
+            float* unp = MODE == MODE_INPUTS ? io.u_norm + ((size_t)b * 2 + f) * nplane + (size_t)rs * PW + j : nullptr;
+            float* pnp = (MODE == MODE_INPUTS && io.p_norm) ? io.p_norm + ((size_t)b * 2 + f) * nplane + (size_t)rs * PW + j : nullptr;
+            const float* su = su_base;
+            const float* sn = sn_base;
+            int s = 0; uint32_t ph = 0;
+            int base = g ? SPLIT * ADV / PER : 0;               // h[k] = W-interpolated coarse row base - 1 + k
+            float h[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) h[k] = yrow(base - 1 + k);
+            auto emit = [&](int q, float pde, bool last_row) {   // epilogue of one fine row (q: row inside the band)
+                if (MODE == MODE_PDEU) {
+                    st_stream(op + (size_t)q * FW, pde);
+                    if (DUPL && dupl) st_stream(op + (size_t)q * FW + PW, pde);
+                    return;
+                }
+                const float uu = su[q * FW];
+                if (MODE == MODE_UPDATE) {
+                    const float nv = HAS_NN ? sn[q * PW] * s0 + m0 : 0.f;
+                    st_stream(op + (size_t)q * FW, HAS_NN ? nv + uu + pde : uu + pde);
+                    if (DUPL && dupl) {
+                        const float ue = su[q * FW + PW];
+                        st_stream(op + (size_t)q * FW + PW, HAS_NN ? nv + ue + pde : ue + pde);
+                    }
+                } else {
+                    if (op) st_stream(op + (size_t)q * FW, pde);
+                    if (op && DUPL && dupl) st_stream(op + (size_t)q * FW + PW, pde);
+                    if (!last_row) {
+                        st_stream(unp + (size_t)q * PW, div_by(uu - m0, s0, rs0));
+                        if (pnp) st_stream(pnp + (size_t)q * PW, div_by(pde - m1, s1, rs1));
+                    }
+                }
+            };
+            auto advance = [&]() {
+                if (MODE != MODE_PDEU) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
+                    if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
+                    else { su += ustep; sn += nstep; }
+                }
+                if (op) op += (size_t)R * FW;
+                if (MODE == MODE_INPUTS) { unp += (size_t)R * PW; if (pnp) pnp += (size_t)R * PW; }
+            };
+            for (int per = 0; per < SPLIT / PER; ++per) {
+#pragma unroll
+                for (int bnd = 0; bnd < PER / R; ++bnd) {
+                    if (MODE != MODE_PDEU) mbar_wait_addr(full_a + 8u * s, ph);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int r = bnd * R + q;              // compile-time after unrolling
+                        const int o = (r * ADV) / PER;
+                        emit(q, h[o] * pw.w[r][0] + h[o + 1] * pw.w[r][1] + h[o + 2] * pw.w[r][2] + h[o + 3] * pw.w[r][3], false);
+                    }
+                    advance();
+                }
+                base += ADV;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) h[k] = k + ADV < NACC ? h[k + ADV] : yrow(base - 1 + k);
+            }
+            if (g == 1) {                                       // row 256 sits on the last coarse node: weights (0,1,0,0)
+                if (MODE != MODE_PDEU) mbar_wait_addr(full_a + 8u * s, ph);
+                emit(0, h[1], true);
+            }
+        };
+        if ((warp & 7) == 0) stream_rows(std::true_type{}); else stream_rows(std::false_type{});
+        return;
+    }
     if (warp >= nconsumers) return;
     const int g = warp / pl.nchunk;
     const int chunk = warp - g * pl.nchunk;

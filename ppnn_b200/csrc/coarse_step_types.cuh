@@ -19,6 +19,21 @@ struct StepIO {
     float m1[2], s1[2];    // pdemean/pdestd (INPUTS)
 };
 
+// Keys-cubic weights of the phases of one prolongation period (kernels specialised for the reference's
+// meshes, 257 -> 33 / 49: every PER fine rows the 4-row coarse window moves on by exactly ADV rows and the
+// PER phases repeat).  Passed by value as a kernel parameter, so that with the period unrolled at compile
+// time the weights are constant-bank operands of the FFMAs.
+struct PhaseWeights { float w[16][4]; };
+
+inline PhaseWeights make_phase_weights(float scale, int per) {
+    PhaseWeights pw;
+    for (int r = 0; r < 16; ++r) {
+        const float s = scale * (float)(r < per ? r : 0);
+        cubic_weights(s - floorf(s), pw.w[r]);
+    }
+    return pw;
+}
+
 struct StepPlan {
     int wmain;             // columns handled by strips (FW-1 when that is a multiple of 32, else FW)
     int nchunk, nband, band_rows;

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PPNN_B200_ABI_VERSION 2
+#define PPNN_B200_ABI_VERSION 3
 
 /* ---- status codes --------------------------------------------------------- */
 #define PPNN_OK            0
@@ -233,6 +233,60 @@ int ppnn_fine_rhs_step(const float* u, const float* v, const float* mu,
                        int endpoint, int rhs_u, int rhs_v,
                        int adv_accuracy, int diff_accuracy,
                        float dt, float dx, float dy, void* stream);
+
+/* ============ Tier B: small explicit solvers, many steps per launch ======== *
+ * One CTA owns one sample; the state stays in registers / shared memory for all
+ * `nsteps` steps of the launch (HBM is touched on entry and exit only).        */
+
+/* 1-D Kuramoto-Sivashinsky generator, classic RK4 (src/operators.py:845-918; f at :883-884 is
+ * rhs.ks1d, src/rhs.py:49-50, plus an optional source term):
+ *   f(u) = -d2udx2(pad u)/dx2 - d4udx4(pad u)/dx4 - 0.5*dudx(pad(u*u))/dx + source
+ *   u <- u + dt*(k1 + 2*k2 + 2*k3 + k4)/6
+ * with diffusion1D('Central', d2_accuracy), diffusion1D('Central_4th', d4_accuracy) and
+ * dudx_1D('Upwind', adv_accuracy) (switch on the sign of u*u, as operators.py:126-127 does).
+ * u, u_out [B, n]; source [n] or NULL.  endpoint != 0: duplicated periodic endpoint, the pad of
+ * operators.py:852-853 (neighbour (i+d) modulo n-1 on the n-point array); endpoint == 0: period n.
+ * dx2, dx4 are the caller's dx**2 and dx2**2 (Python doubles in the reference), rounded to fp32.
+ * n <= 8192.  u_out may alias u.                                                             */
+int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, int B, int n, int endpoint,
+                  int nsteps, int adv_accuracy, int d2_accuracy, int d4_accuracy,
+                  float dt, float dx, float dx2, float dx4, void* stream);
+
+/* 2-D Kuramoto-Sivashinsky generator, classic RK4 (src/operators.py:750-843; f at :806-809):
+ *   f(u) = -c2*d2udx2(u)/dx2 - c2*d2udy2(u)/dy2 - d4udx4(u)/dx4 - d4udy4(u)/dy4
+ *          - mixed_scale*d2udy2(pad(d2udx2(pad u))) - mixed_scale*d2udx2(pad(d2udy2(pad u)))
+ *          - 0.5*dudx(pad(u*u))/dx - 0.5*dudy(pad(u*u))/dy
+ * (reference: c2 = 0.1, mixed_scale = 1: the mixed term is NOT divided by dx2*dy2 there), Central2 /
+ * Central4 / Upwind1 stencils, every pad the duplicated-endpoint wrap of operators.py:761-765.
+ * u, u_out [B, H, W]; 4*H*W floats must fit in shared memory (H*W <= 14528, e.g. 120^2), else
+ * PPNN_E_TOOBIG: compose the step from the Tier-A operators.  u_out may alias u.             */
+int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, int endpoint, int nsteps,
+                  int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
+                  float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,
+                  void* stream);
+
+/* padder.__call__ (Bv/data.py:25-28): out [B, n+2] = [ghost_l | u | ghost_r] with
+ * ghost = (cls == 0)*bv + (cls == 1)*(u_edge + bv*dx); cls [B,2] int32 (0 Dirichlet, 1 Neumann),
+ * bv [B,2].                                                                                   */
+int ppnn_heat1d_pad(const float* u, const int* cls, const float* bv, float* out,
+                    int B, int n, float dx, void* stream);
+
+/* The generator loop of Bv/data.py:92-97, `nsteps` steps in one launch:
+ *   up = padder(u, cls, bv);  u <- u + diffusion1D(accuracy=2)(up)/dx2*dt
+ * padded_out (may be NULL) receives up = padder(u_in) BEFORE the first step (what the loop saves
+ * every `saveevery` steps), sample b at padded_out + b*padded_stride, n+2 floats; u_out [B, n]
+ * (may be NULL if only the padded snapshot is wanted; may alias u).                           */
+int ppnn_heat1d_bc_steps(const float* u, const int* cls, const float* bv, float* u_out,
+                         float* padded_out, long padded_stride, int B, int n, int nsteps,
+                         float dt, float dx, float dx2, void* stream);
+
+/* genforward(...).forward (Bv/data.py:39-51), the 1-D analogue of pde_du with ghost cells:
+ *   uc = linear_down(u);  uc1 = padder_c(uc[1:-1] + diffusion1D(uc)/cdx2*dt);  out = linear_up(uc1) - u
+ * u, out [B, nf] (the PADDED fine state, nf = n+2), nc coarse points (F.interpolate with
+ * align_corners=True: floor(nf*scale)).  out must not alias u.                                */
+int ppnn_heat1d_coarse_increment(const float* u, const int* cls, const float* bv, float* out,
+                                 int B, int nf, int nc, float dt, float cdx, float cdx2,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,8 @@ Reference lines followed (paths relative to the reference checkout):
 * PDE-only fine rollout .............. post_process/test_predict_2Dp.py:116
 * coarse-only solver ................. post_process/test_2D_csolver.py:56-75
 * "iter" variant ..................... post_process/test2D2.py:70-91
+* 2-D / 1-D Kuramoto-Sivashinsky RK4 . src/operators.py:750-843, 845-918 (commented generators)
+* 1-D heat step with ghost cells ..... Bv/data.py:9-51, 92-97
 
 All functions work in whatever dtype their tensor arguments carry (fp32 for
 parity, fp64 for the noise-floor reference).
@@ -430,6 +432,89 @@ def fine_burgers_run(u, v, mu, nsteps: int, every: int = 200, **kw):
             su.append(u.clone())
             sv.append(v.clone())
     return u, v, su, sv
+
+
+# --------------------------------------------------------------------------
+# Small explicit solvers: Kuramoto-Sivashinsky with RK4 (operators.py:750-918) and
+# the 1-D heat equation with Dirichlet / Neumann ghost cells (Bv/data.py).
+# --------------------------------------------------------------------------
+def rk4_step(f: Callable, u: torch.Tensor, dt: float) -> torch.Tensor:
+    """operators.py:805-815 / :882-890."""
+    k1 = f(u)
+    k2 = f(u + dt * k1 / 2)
+    k3 = f(u + dt * k2 / 2)
+    k4 = f(u + dt * k3)
+    return u + dt * (k1 + 2 * k2 + 2 * k3 + k4) / 6
+
+
+def ks2d_rhs(u, dx: float, dy: float, c2: float = 0.1, mixed_scale: float = 1.0,
+             adv_acc: int = 3, d2_acc: int = 6, d4_acc: int = 4, period_endpoint: bool = True):
+    """``f`` of operators.py:806-809 on [B,1,H,W] (pads :761-765; operators :797-802).  As written there the
+    mixed term is not divided by dx2*dy2 (``mixed_scale = 1``) and the second derivatives carry 0.1."""
+    h = adv_acc
+    assert h == d2_acc // 2 == d4_acc // 2 + 1, "the generator pads one halo for every stencil"
+    px, py = (fine_wrap_x, fine_wrap_y) if period_endpoint else (wrap_x, wrap_y)
+    dx2, dy2 = dx ** 2, dy ** 2
+    dx4, dy4 = dx2 ** 2, dy2 ** 2
+    L2x = lambda w: stencil2d(px(w, h), "Central2", d2_acc, 2)
+    L2y = lambda w: stencil2d(py(w, h), "Central2", d2_acc, 3)
+    m = mixed_scale
+    mixed1 = L2y(L2x(u)) if m == 1.0 else m * L2y(L2x(u))
+    mixed2 = L2x(L2y(u)) if m == 1.0 else m * L2x(L2y(u))
+    return (- c2 * L2x(u) / dx2 - c2 * L2y(u) / dy2 - stencil2d(px(u, h), "Central4", d4_acc, 2) / dx4
+            - stencil2d(py(u, h), "Central4", d4_acc, 3) / dy4 - mixed1 - mixed2
+            - 0.5 * upwind2d(px(u * u, h), adv_acc, 2) / dx - 0.5 * upwind2d(py(u * u, h), adv_acc, 3) / dy)
+
+
+def ks2d_rk4_step(u, dt: float = 1e-3, dx: float = 0.39269908169872414, dy: Optional[float] = None, **kw):
+    dy = dx if dy is None else dy
+    return rk4_step(lambda w: ks2d_rhs(w, dx, dy, **kw), u, dt)
+
+
+def ks1d_rhs(u, dx: float, source=None, adv_acc: int = 3, d2_acc: int = 6, d4_acc: int = 4,
+             period_endpoint: bool = True):
+    """``f`` of operators.py:883-884 on [B,1,n]: rhs.ks1d on the pad of :852-853, plus the source term."""
+    h = adv_acc
+    assert h == d2_acc // 2 == d4_acc // 2 + 1
+    if period_endpoint:
+        pad = lambda w: torch.cat((w[:, :, -h - 1:-1], w, w[:, :, 1:h + 1]), dim=2)
+    else:
+        pad = lambda w: torch.cat((w[:, :, -h:], w, w[:, :, :h]), dim=2)
+    dx2 = dx ** 2
+    dx4 = dx2 ** 2
+    r = ks1d(pad(u), None, pad(u), dx, dx2, dx4, adv_acc=adv_acc, d2_acc=d2_acc, d4_acc=d4_acc)
+    return r if source is None else r + source
+
+
+def ks1d_rk4_step(u, dt: float = 1e-4, dx: float = 0.39269908169872414, source=None, **kw):
+    return rk4_step(lambda w: ks1d_rhs(w, dx, source, **kw), u, dt)
+
+
+def bv_pad(u, cls, bv, dx):
+    """padder.__call__ (Bv/data.py:25-28)."""
+    pad2 = lambda w, b: w + b * dx
+    bcl = (cls[..., :1] == 0) * bv[..., :1] + (cls[..., :1] == 1) * pad2(u[..., :1], bv[..., :1])
+    bcr = (cls[..., 1:] == 0) * bv[..., 1:] + (cls[..., 1:] == 1) * pad2(u[..., -1:], bv[..., 1:])
+    return torch.cat([bcl, u, bcr], dim=-1)
+
+
+def bv_heat_run(u, cls, bv, nsteps: int, saveevery: int, dt, dx, dx2):
+    """The generator loop of Bv/data.py:92-98 -> (final u, stacked padded snapshots [B,T,1,n+2])."""
+    results = []
+    for t in range(nsteps):
+        up = bv_pad(u, cls, bv, dx)
+        u = u + stencil1d(up, "Central", 2) / dx2 * dt
+        if t % saveevery == 0:
+            results.append(up)
+    return u, torch.stack(results, dim=1)
+
+
+def bv_coarse_increment(u, cls, bv, scale: float, dt, cdx, cdx2):
+    """genforward(...).forward (Bv/data.py:39-51) with the callables of :113-117."""
+    uc = F.interpolate(u, scale_factor=scale, mode="linear", align_corners=True)
+    cdu = stencil1d(uc, "Central", 2) / cdx2 * dt
+    uc1 = bv_pad(uc[..., 1:-1] + cdu, cls, bv, cdx)
+    return F.interpolate(uc1, scale_factor=1 / scale, mode="linear", align_corners=True) - u
 
 
 def fourier_initial_condition(coef: torch.Tensor, n: int, modes: int = 4) -> torch.Tensor:

@@ -10,6 +10,8 @@ on PYTHONPATH, or import from here):
     ppnn_b200.utility.utils  mesh_convertor, model_count
 Tier B (fully fused):
     ppnn_b200.fused          CoarseStep (pde_du, step_inputs, step_update, rollouts), FineBurgers, FineRhsSolver
+    ppnn_b200.solvers        KS1D, KS2D (Kuramoto-Sivashinsky RK4), HeatBC1D, HeatCoarseIncrement (Bv/): many steps per launch
+    ppnn_b200.bv             padder, denormBV, genforward (mirror of Bv/data.py)
     ppnn_b200.datagen        sharded dataset generation (python -m ppnn_b200.datagen)
     ppnn_b200.dist           sample sharding / global statistics helpers
 
@@ -21,3 +23,4 @@ from .fused import CoarseStep, FineBurgers, FineRhsSolver, HostStepPipeline, Rol
 
 __all__ = ["CoarseStep", "FineBurgers", "FineRhsSolver", "operators", "rhs", "utility"]
 from .dataset import PdeDataset  # noqa: F401
+from .solvers import KS1D, KS2D, HeatBC1D, HeatCoarseIncrement  # noqa: F401

@@ -14,8 +14,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPNN_B200_LIB") or os.path.join(_HERE, "libppnn_b200.so")
-ABI_VERSION = 2
-E_NULL, E_SHAPE = -1, -2          # status codes of include/ppnn_b200.h used by the host code
+ABI_VERSION = 3
+E_NULL, E_SHAPE, E_TOOBIG = -1, -2, -5   # status codes of include/ppnn_b200.h used by the host code
 
 # enums of include/ppnn_b200.h
 CENTRAL1, CENTRAL2, CENTRAL4, FORWARD1, BACKWARD1, UPWIND1 = range(6)
@@ -65,6 +65,11 @@ _SIGNATURES = {
     "ppnn_fine_burgers_step": (C.c_int, [_P] * 5 + [C.c_int] * 7 + [C.c_float] * 3 + [_P]),
     "ppnn_fourier_ic": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "ppnn_fine_rhs_step": (C.c_int, [_P] * 5 + [C.c_int] * 8 + [C.c_float] * 3 + [_P]),
+    "ppnn_ks1d_rk4": (C.c_int, [_P] * 3 + [C.c_int] * 7 + [C.c_float] * 4 + [_P]),
+    "ppnn_ks2d_rk4": (C.c_int, [_P] * 2 + [C.c_int] * 8 + [C.c_float] * 9 + [_P]),
+    "ppnn_heat1d_pad": (C.c_int, [_P] * 4 + [C.c_int] * 2 + [C.c_float, _P]),
+    "ppnn_heat1d_bc_steps": (C.c_int, [_P] * 5 + [C.c_long] + [C.c_int] * 3 + [C.c_float] * 3 + [_P]),
+    "ppnn_heat1d_coarse_increment": (C.c_int, [_P] * 4 + [C.c_int] * 3 + [C.c_float] * 3 + [_P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -359,8 +359,137 @@ def gen_fine():
     save("fine.npz", **out)
 
 
+# ---------------------------------------------------------------- small explicit solvers
+def gen_solvers():
+    """The commented Kuramoto-Sivashinsky generators of operators.py:750-918 (closures re-typed around the
+    imported operator classes) and the live Bv/data.py code (imported: padder, denormBV, genforward)."""
+    pi = np.pi
+    out = {}
+    # ---- 2-D KS, operators.py:761-815
+    g = torch.Generator().manual_seed(707)
+    x = torch.linspace(0, 8 * pi, 65)
+    x, y = torch.meshgrid(x, x, indexing="ij")
+    x = x.unsqueeze(0).unsqueeze(0).repeat([2, 1, 1, 1])
+    y = y.unsqueeze(0).unsqueeze(0).repeat([2, 1, 1, 1])
+    dt, dx = 1e-3, pi / 8
+    dy = dx
+    dx2, dy2 = dx ** 2, dy ** 2
+    dx4, dy4 = dx2 ** 2, dy2 ** 2
+    initu = torch.cos(x / 4) * (1 + torch.sin(y / 4))                    # :787
+    initu[1] += 0.3 * torch.randn(1, 1, 1, generator=g) * torch.sin(x[1] / 2 + y[1] / 4)
+    initu[1, 0, 10, 12] = 0.0                                            # u*u == 0: the '<= 0' upwind branch
+    initu[1, 0, 0, 0] = 0.0
+    dudx, dudy = ref_ops.dudx_2D('Upwind1', accuracy=3), ref_ops.dudy_2D('Upwind1', accuracy=3)
+    d2udx2, d2udy2 = ref_ops.d2udx2_2D('Central2', accuracy=6), ref_ops.d2udy2_2D('Central2', accuracy=6)
+    d4udx4, d4udy4 = ref_ops.d2udx2_2D('Central4', accuracy=4), ref_ops.d2udy2_2D('Central4', accuracy=4)
+
+    def padbcx(uinner):
+        return torch.cat((uinner[:, :, -4:-1], uinner, uinner[:, :, 1:4]), dim=2)
+
+    def padbcy(uinner):
+        return torch.cat((uinner[:, :, :, -4:-1], uinner, uinner[:, :, :, 1:4]), dim=3)
+
+    def rk4(u):
+        def f(u):
+            return - .1*d2udx2(padbcx(u))/dx2 - .1*d2udy2(padbcy(u))/dy2 - d4udx4(padbcx(u))/dx4 \
+                - d4udy4(padbcy(u))/dy4 - d2udy2(padbcy(d2udx2(padbcx(u)))) - d2udx2(padbcx(d2udy2(padbcy(u)))) \
+                - 0.5*dudx(padbcx(u*u))/dx - 0.5*dudy(padbcy(u*u))/dy
+        k1 = f(u)
+        k2 = f(u + dt*k1/2)
+        k3 = f(u + dt*k2/2)
+        k4 = f(u + dt*k3)
+        return u + dt*(k1 + 2*k2 + 2*k3 + k4)/6, k1
+
+    u = initu
+    out["ks2d/u0"] = initu
+    for i in range(3):
+        u, k1 = rk4(u)
+        if i == 0:
+            out["ks2d/f0"] = k1
+        out[f"ks2d/u{i + 1}"] = u
+
+    # ---- 1-D KS, operators.py:852-890
+    nb = 4
+    x = torch.linspace(0, 8 * pi, 129).unsqueeze(0).unsqueeze(0).repeat([nb, 1, 1])
+    dt1 = 1e-4
+    phi0 = torch.randn((nb, 1, 1), generator=g)
+    phi1 = torch.randn((nb, 1, 1), generator=g)
+    initu = torch.cos(x / 16 + phi0) * (1 + torch.sin(x / 16 + phi1)) + torch.exp(-25 * (x / 8 / pi - 0.5) ** 2)   # :869
+    initu[2, 0, 40] = 0.0
+    initu[3, 0, 128] = 0.0
+    dudx1 = ref_ops.dudx_1D('Upwind', accuracy=3)
+    d2udx2_1 = ref_ops.diffusion1D('Central', accuracy=6)
+    d4udx4_1 = ref_ops.diffusion1D('Central_4th', accuracy=4)
+
+    def padbc(uinner):
+        return torch.cat((uinner[:, :, -4:-1], uinner, uinner[:, :, 1:4]), dim=2)
+
+    source = 0.1 * torch.exp(-(x - 4 * pi) ** 2 / 2)
+
+    def rk4_1d(u):
+        def f(u):
+            return - d2udx2_1(padbc(u))/dx2 - d4udx4_1(padbc(u))/dx4 - 0.5*dudx1(padbc(u*u))/dx + 0.1*torch.exp(-(x - 4*pi)**2/2)
+        k1 = f(u)
+        k2 = f(u + dt1*k1/2)
+        k3 = f(u + dt1*k2/2)
+        k4 = f(u + dt1*k3)
+        return u + dt1*(k1 + 2*k2 + 2*k3 + k4)/6, k1
+
+    u = initu
+    out["ks1d/u0"], out["ks1d/source"] = initu, source[0, 0]
+    for i in range(3):
+        u, k1 = rk4_1d(u)
+        if i == 0:
+            out["ks1d/f0"] = k1
+            # the same right-hand side through rhs.ks1d (rhs.py:49-50), without the source term
+            out["ks1d/rhs_ks1d"] = ref_rhs.ks1d(padbc(initu), None, dudx1, d2udx2_1, d4udx4_1, padbc(initu), dx, dx2, dx2 ** 2)
+        out[f"ks1d/u{i + 1}"] = u
+
+    # ---- Bv/data.py: padder, generator loop (:77-98), genforward (:113-121); imported, not re-typed
+    sys.path.insert(0, REF)
+    from Bv.data import padder as ref_padder, denormBV as ref_denorm, genforward as ref_genforward
+    from torch.nn.functional import interpolate as interp
+    L = 16 * torch.pi
+    Nx = 2 ** 7 - 2
+    scale = 1 / 4
+    Nb = 8
+    dtb = 0.01
+    saveevery = 50
+    ldt = dtb * saveevery
+    xb = torch.linspace(0, L, Nx + 2)[1:-1]
+    dxb = xb[1] - xb[0]
+    dxb2 = dxb ** 2
+    u0 = 0
+    for i in range(16):
+        for _ in range(4):
+            u0 = u0 + (torch.rand(size=(Nb, 1), generator=g) - 0.5) * np.sin(i / 16 * xb[None, ] + L * torch.rand(size=(Nb, 1), generator=g))
+    BV = torch.rand(size=(Nb, 1, 2), generator=g) * 2 - 1
+    cls = torch.tensor([[0, 0], [0, 1], [1, 0], [1, 1], [1, 1], [0, 0], [1, 0], [0, 1]]).reshape(Nb, 1, 2)
+    BVr = ref_denorm(BV, cls)
+    diffuer = ref_ops.diffusion1D(accuracy=2)
+    pad = ref_padder(dxb)
+    u = u0[:, None].float()
+    results = []
+    for t in range(151):
+        up = pad(u, cls, BVr)
+        u = u + diffuer(up) / dxb2 * dtb
+        if t % saveevery == 0:
+            results.append(up)
+    results = torch.stack(results, dim=1)
+    downfn = lambda w: interp(w, scale_factor=scale, mode='linear', align_corners=True)
+    upfn = lambda w: interp(w, scale_factor=1 / scale, mode='linear', align_corners=True)
+    cdx = dxb / scale
+    cdx2 = cdx ** 2
+    fn = ref_genforward(diffuer, downfn, upfn, ref_padder(cdx), ldt, cdx2)
+    pdeu = torch.stack([fn(results[:, t], cls, BVr) for t in range(results.shape[1])], dim=1)
+    out.update({"bv/u0": u0[:, None].float(), "bv/cls": cls, "bv/BV": BV, "bv/BVr": BVr, "bv/dx": dxb, "bv/dt": dtb,
+                "bv/saveevery": saveevery, "bv/scale": scale, "bv/results": results, "bv/u_final": u,
+                "bv/pdeu": pdeu, "bv/pad0": pad(u0[:, None].float(), cls, BVr)})
+    save("solvers.npz", **out)
+
+
 if __name__ == "__main__":
     gens = dict(operators=gen_operators, rhs=gen_rhs, mesh=gen_mesh, pde_du=gen_pde_du, fine=gen_fine,
-                dataset=gen_dataset, step_257=gen_step_257)
+                dataset=gen_dataset, step_257=gen_step_257, solvers=gen_solvers)
     for which in (sys.argv[1:] or list(gens)):          # e.g. `make_golden.py dataset` regenerates one file
         gens[which]()

@@ -61,6 +61,19 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert l.ppnn_fine_burgers_step(1, 2, 3, 1, 5, 1, 33, 33, 1, 0, 3, 6, 1e-4, .01, .01, None) == -6   # alias
     assert l.ppnn_fine_burgers_step(1, 2, 3, 4, 5, 1, 33, 33, 1, 9, 3, 6, 1e-4, .01, .01, None) == -6   # mode
     assert l.ppnn_pde_du_fwd(ctypes.byref(cfg), 1, 1, 1, 0, None) == 0                     # empty batch
+    # small on-chip solvers
+    assert l.ppnn_ks1d_rk4(None, None, 1, 1, 129, 1, 1, 3, 6, 4, 1e-4, .4, .16, .0256, None) == -1      # NULL
+    assert l.ppnn_ks1d_rk4(1, None, 1, 1, 129, 1, 1, 3, 5, 4, 1e-4, .4, .16, .0256, None) == -3         # accuracy
+    assert l.ppnn_ks1d_rk4(1, None, 1, 1, 6, 1, 1, 3, 6, 4, 1e-4, .4, .16, .0256, None) == -2           # period <= 2*halo
+    assert l.ppnn_ks1d_rk4(1, None, 1, 1, 9000, 1, 1, 3, 6, 4, 1e-4, .4, .16, .0256, None) == -5        # too big
+    assert l.ppnn_ks1d_rk4(1, None, 1, 0, 129, 1, 1, 3, 6, 4, 1e-4, .4, .16, .0256, None) == 0          # empty batch
+    assert l.ppnn_ks2d_rk4(1, 1, 1, 129, 129, 1, 1, 3, 6, 4, .1, 1., 1e-3, .4, .4, .16, .16, .0256, .0256, None) == -5
+    assert l.ppnn_ks2d_rk4(1, 1, 1, 65, 65, 1, 1, 4, 6, 4, .1, 1., 1e-3, .4, .4, .16, .16, .0256, .0256, None) == -3
+    assert l.ppnn_heat1d_pad(1, None, 1, 1, 2, 126, .4, None) == -1
+    assert l.ppnn_heat1d_bc_steps(1, 1, 1, None, None, 0, 2, 126, 5, .01, .4, .16, None) == -1          # no output at all
+    assert l.ppnn_heat1d_bc_steps(1, 1, 1, 1, 1, 100, 2, 126, 5, .01, .4, .16, None) == -2              # snapshot stride < n+2
+    assert l.ppnn_heat1d_coarse_increment(1, 1, 1, 1, 2, 128, 32, .5, 1.6, 2.56, None) == -6            # out aliases u
+    assert l.ppnn_heat1d_coarse_increment(1, 1, 1, 2, 2, 128, 2, .5, 1.6, 2.56, None) == -2             # coarse mesh < 3
 
 
 def test_reference_interface_names_defaults_and_asserts(lib):

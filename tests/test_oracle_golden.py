@@ -193,3 +193,31 @@ def test_staged_reference_is_unmodified_and_agrees_with_golden_and_port():
     assert_parity(upd, g["rd_p/update"], TOL, "staged reference update")
     port = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
     assert_parity(O.ppnn_update(g["u"], port.pde_du(g["u"], g["rd_p/mu"]), g["nn"], g["outmean"], g["outstd"]), upd, TOL, "port")
+
+
+def test_small_solvers_ks_rk4_and_bv_heat():
+    """Kuramoto-Sivashinsky RK4 generators (operators.py:750-918) and the Bv/ heat step with ghost cells
+    (Bv/data.py): oracle restatement vs the reference's own lines / imported code (solvers.npz)."""
+    g = load_golden("solvers.npz")
+    u = g["ks2d/u0"]
+    assert_parity(O.ks2d_rhs(u, np.pi / 8, np.pi / 8), g["ks2d/f0"], TOL, "ks2d f")
+    for i in range(3):
+        u = O.ks2d_rk4_step(u, 1e-3, np.pi / 8)
+        assert_parity(u, g[f"ks2d/u{i + 1}"], TOL, f"ks2d step {i + 1}")
+    u, src = g["ks1d/u0"], g["ks1d/source"].reshape(1, 1, -1)
+    assert_parity(O.ks1d_rhs(u, np.pi / 8, src), g["ks1d/f0"], TOL, "ks1d f")
+    assert_parity(O.ks1d_rhs(u, np.pi / 8, None), g["ks1d/rhs_ks1d"], TOL, "rhs.ks1d")
+    for i in range(3):
+        u = O.ks1d_rk4_step(u, 1e-4, np.pi / 8, src)
+        assert_parity(u, g[f"ks1d/u{i + 1}"], TOL, f"ks1d step {i + 1}")
+    cls, bvr, dx = g["bv/cls"], g["bv/BVr"], g["bv/dx"]
+    assert torch.equal(bvr, (cls == 1) * g["bv/BV"] + (cls == 0) * 5 * g["bv/BV"])        # denormBV
+    assert_parity(O.bv_pad(g["bv/u0"], cls, bvr, dx), g["bv/pad0"], TOL, "padder")
+    uf, res = O.bv_heat_run(g["bv/u0"], cls, bvr, 151, int(g["bv/saveevery"]), float(g["bv/dt"]), dx, dx ** 2)
+    assert_parity(res, g["bv/results"], TOL, "bv generator snapshots")
+    assert_parity(uf, g["bv/u_final"], TOL, "bv final state")
+    scale = float(g["bv/scale"])
+    cdx = dx / scale
+    for t in range(res.shape[1]):
+        inc = O.bv_coarse_increment(g["bv/results"][:, t], cls, bvr, scale, float(g["bv/dt"]) * int(g["bv/saveevery"]), cdx, cdx ** 2)
+        assert_parity(inc, g["bv/pdeu"][:, t], TOL, f"genforward t={t}")

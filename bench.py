@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            (our arm)
     python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+    python bench.py --sweep [quick|full] --gpus N            (BASELINE configs[4]: roofline sweep table)
 
 Workload (BASELINE.json configs[1], cases/RD_pPDE.yaml): one "step" is ONE launch
 of the fused coarse-grid step kernel over a batch of B samples per GPU
@@ -57,6 +58,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel timings")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-batch", type=int, default=240)
+    ap.add_argument("--sweep", nargs="?", const="full", choices=["quick", "full"],
+                    help="BASELINE configs[4]: stencil roofline sweep (markdown table on stdout) instead of the bench line")
     return ap.parse_args()
 
 
@@ -232,6 +235,104 @@ def workload_config(B, n):
          "parallelism": f"batch-sharded x{n}, no data-path collective",
          "l2": "inputs (3.0 GB per GPU) exceed the 126 MB L2; no flush needed"}
     return c
+
+
+# ----------------------------------------------------------------------------- config 5: roofline sweep
+def cpu_sweep_fn():
+    """CPU-reference column of the sweep: the staged reference's own operator / rhs objects (oracle/_ref) on the
+    host cores, per (op, N) on a bounded batch (>= 4 M grid points, at least one sample), G units/s."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_closures as R
+    if not R.available():
+        return None
+    m = R.modules()
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    o = m.operators
+    op6 = (o.dudx_2D("Upwind1", 3), o.dudy_2D("Upwind1", 3), o.d2udx2_2D("Central2", 6), o.d2udy2_2D("Central2", 6))
+    d2x2, dy1 = o.d2udx2_2D("Central2", 2), o.dudy_2D("Upwind1", 1)
+
+    def padx(w, h):
+        return torch.cat((w[:, :, -h:], w, w[:, :, :h]), dim=2)
+
+    def pady(w, h):
+        return torch.cat((w[:, :, :, -h:], w, w[:, :, :, :h]), dim=3)
+
+    def cpu(name, N):
+        B = max(1, (1 << 22) // (N * N))
+        g = torch.Generator().manual_seed(1)
+        u = torch.rand(B, 1, N, N, generator=g) - 0.4
+        v = torch.rand(B, 1, N, N, generator=g) - 0.4
+        mu = torch.full((B, 1, 1, 1), 0.04)
+        dx = 0.0125
+        ux, uy, ux1, uy1 = padx(u, 3), pady(u, 3), padx(u, 1), pady(u, 1)
+
+        def gen_step():                                  # operators.py:466-475 (true-periodic pads on these meshes)
+            ax, ay = padx(u, 3), pady(u, 3)
+            padx(v, 3), pady(v, 3)                       # :469-470: computed by the reference, unused as written
+            u * u + v * v                                # :472
+            un = u + 1e-4 * m.rhs.burgers2Dpu(u, v, mu, *op6, ax, ay, dx, dx, dx * dx, dx * dx)
+            return un, v + 1e-4 * m.rhs.burgers2Dpv(un, v, mu, *op6, ax, ay, dx, dx, dx * dx, dx * dx)
+        fns = {"d2udx2_2D Central2 acc 6 (x)": lambda: op6[2](ux), "d2udy2_2D Central2 acc 6 (y)": lambda: op6[3](uy),
+               "dudx_2D Upwind1 acc 3 (x)": lambda: op6[0](ux), "dudy_2D Upwind1 acc 3 (y)": lambda: op6[1](uy),
+               "d2udx2_2D Central2 acc 2 (x)": lambda: d2x2(ux1), "dudy_2D Upwind1 acc 1 (y)": lambda: dy1(uy1),
+               "rhs.burgers2Dpu fused (acc 3/6)": lambda: m.rhs.burgers2Dpu(u, v, mu, *op6, ux, uy, dx, dx, dx * dx, dx * dx),
+               "fused Burgers step (u,v)": gen_step}
+        fn = fns[name]
+        units = 2 if name.startswith("fused Burgers step") else 1
+        with torch.no_grad():
+            fn()
+            t0, reps = time.perf_counter(), 0
+            while reps < 2 or (time.perf_counter() - t0 < 0.25 and reps < 50):
+                fn()
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+        return units * B * N * N / dt / 1e9, cores
+    return cpu
+
+
+def run_sweep(args):
+    """`bench.py --sweep [quick|full] [--gpus N]`: tools/sweep.py on N GPUs (batch-sharded, no communication) with
+    the reference's CPU implementation of every op timed beside it on rank 0."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --sweep: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep as SW
+    cpu = None if args.no_cpu else cpu_sweep_fn()
+    if rank == 0:
+        print(f"# Stencil roofline sweep (BASELINE configs[4]), {world} x B200\n\n"
+              f"`bench.py --sweep {args.sweep} --gpus {world}`: fp32, CUDA events, max over ranks, 6-20 repetitions after 3 "
+              f"warm-ups; N x N periodic grids x GLOBAL batch B sharded over the GPUs (cells with B < GPUs skipped).  "
+              f"CPU reference = the reference's own operator / rhs modules (oracle/_ref) on the host's "
+              f"{os.cpu_count()} hardware threads, per (op, N) on a bounded batch (>= 4 M grid points); units = output "
+              f"points (operators, rhs) or point-updates (step).\n", flush=True)
+    SW.sweep(dev, world, rank, quick=args.sweep == "quick", cpu=cpu, barrier=barrier, max_over_ranks=max_over_ranks)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------- config 3 / config 4 legs
@@ -653,7 +754,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.sweep:
+        run_sweep(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -252,6 +252,11 @@ int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, int B, int 
                   int nsteps, int adv_accuracy, int d2_accuracy, int d4_accuracy,
                   float dt, float dx, float dx2, float dx4, void* stream);
 
+/* f(u) alone (the `f` closure of operators.py:883-884): f_out [B, n], must not alias u.          */
+int ppnn_ks1d_rhs(const float* u, const float* source, float* f_out, int B, int n, int endpoint,
+                  int adv_accuracy, int d2_accuracy, int d4_accuracy,
+                  float dx, float dx2, float dx4, void* stream);
+
 /* 2-D Kuramoto-Sivashinsky generator, classic RK4 (src/operators.py:750-843; f at :806-809):
  *   f(u) = -c2*d2udx2(u)/dx2 - c2*d2udy2(u)/dy2 - d4udx4(u)/dx4 - d4udy4(u)/dy4
  *          - mixed_scale*d2udy2(pad(d2udx2(pad u))) - mixed_scale*d2udx2(pad(d2udy2(pad u)))
@@ -264,6 +269,11 @@ int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, int endpoin
                   int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
                   float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,
                   void* stream);
+
+/* f(u) alone (the `f` closure of operators.py:806-809): f_out [B, H, W], must not alias u.      */
+int ppnn_ks2d_rhs(const float* u, float* f_out, int B, int H, int W, int endpoint,
+                  int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
+                  float dx, float dy, float dx2, float dy2, float dx4, float dy4, void* stream);
 
 /* padder.__call__ (Bv/data.py:25-28): out [B, n+2] = [ghost_l | u | ghost_r] with
  * ghost = (cls == 0)*bv + (cls == 1)*(u_edge + bv*dx); cls [B,2] int32 (0 Dirichlet, 1 Neumann),

@@ -66,6 +66,8 @@ _SIGNATURES = {
     "ppnn_fourier_ic": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "ppnn_fine_rhs_step": (C.c_int, [_P] * 5 + [C.c_int] * 8 + [C.c_float] * 3 + [_P]),
     "ppnn_ks1d_rk4": (C.c_int, [_P] * 3 + [C.c_int] * 7 + [C.c_float] * 4 + [_P]),
+    "ppnn_ks1d_rhs": (C.c_int, [_P] * 3 + [C.c_int] * 6 + [C.c_float] * 3 + [_P]),
+    "ppnn_ks2d_rhs": (C.c_int, [_P] * 2 + [C.c_int] * 7 + [C.c_float] * 8 + [_P]),
     "ppnn_ks2d_rk4": (C.c_int, [_P] * 2 + [C.c_int] * 8 + [C.c_float] * 9 + [_P]),
     "ppnn_heat1d_pad": (C.c_int, [_P] * 4 + [C.c_int] * 2 + [C.c_float, _P]),
     "ppnn_heat1d_bc_steps": (C.c_int, [_P] * 5 + [C.c_long] + [C.c_int] * 3 + [C.c_float] * 3 + [_P]),

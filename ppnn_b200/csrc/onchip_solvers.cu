@@ -37,6 +37,7 @@ __device__ __forceinline__ int wrap_axis(int j, int n, int P) { return j < 0 ? j
 struct Ks1dParams {
     const float* u; const float* source; float* out;
     int n, P, nsteps;
+    int rhs_only;        // write f(u) instead of stepping (the reference's `f` closure)
     float dt, dx, rdx, dx2, rdx2, dx4, rdx4;
     CenteredTaps d2, d4, af, ab;
 };
@@ -101,6 +102,15 @@ ks1d_rk4_kernel(const Ks1dParams p) {
         }
     }
     __syncthreads();
+    if (p.rhs_only) {
+        float* o = p.out + (size_t)blockIdx.x * p.n;
+#pragma unroll
+        for (int q = 0; q < PTS; ++q) {
+            const int i = threadIdx.x + q * T;
+            if (i < p.n) o[i] = ks1d_rhs<HALO, true>(p, cur, i, SRC[q]);
+        }
+        return;
+    }
     for (int step = 0; step < p.nsteps; ++step) {
 #pragma unroll
         for (int stage = 0; stage < 4; ++stage) {
@@ -149,6 +159,7 @@ static int launch_ks1d(const Ks1dParams& p, int B, void* stream) {
 struct Ks2dParams {
     const float* u; float* out;
     int H, W, PH, PW, nsteps;
+    int rhs_only;        // write f(u) instead of stepping (the reference's `f` closure)
     float invW;
     float c2, mixed, dt;
     float dx, rdx, dy, rdy, dx2, rdx2, dy2, rdy2, dx4, rdx4, dy4, rdy4;
@@ -230,6 +241,21 @@ ks2d_rk4_kernel(const Ks2dParams p) {
         if (idx < N) { U[q] = uin[idx]; cur[idx] = U[q]; }
     }
     __syncthreads();
+    if (p.rhs_only) {
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < N; idx += T) {
+            const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
+            ks2d_second<HALO, true>(p, cur, i, j, LX + idx, LY + idx);
+        }
+        __syncthreads();
+        float* o = p.out + (size_t)blockIdx.x * N;
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < N; idx += T) {
+            const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
+            o[idx] = ks2d_rhs<HALO, true>(p, cur, LX, LY, i, j);
+        }
+        return;
+    }
     for (int step = 0; step < p.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
@@ -440,9 +466,9 @@ heat1d_pad_kernel(const float* __restrict__ u, const int* __restrict__ cls, cons
 
 using namespace ppnn;
 
-extern "C" int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, int B, int n, int endpoint,
-                             int nsteps, int adv_accuracy, int d2_accuracy, int d4_accuracy,
-                             float dt, float dx, float dx2, float dx4, void* stream) {
+static int ks1d_entry(const float* u, const float* source, float* u_out, int B, int n, int endpoint,
+                      int nsteps, int rhs_only, int adv_accuracy, int d2_accuracy, int d4_accuracy,
+                      float dt, float dx, float dx2, float dx4, void* stream) {
     if (!u || !u_out) return PPNN_E_NULL;
     if (B < 0 || nsteps < 0) return PPNN_E_SHAPE;
     Ks1dParams p;
@@ -452,7 +478,7 @@ extern "C" int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, 
     p.n = n; p.P = endpoint ? n - 1 : n;
     if (p.P <= 2 * halo) return PPNN_E_SHAPE;
     if (B == 0) return PPNN_OK;
-    p.u = u; p.source = source; p.out = u_out; p.nsteps = nsteps;
+    p.u = u; p.source = source; p.out = u_out; p.nsteps = nsteps; p.rhs_only = rhs_only;
     p.dt = dt; p.dx = dx; p.rdx = 1.f / dx; p.dx2 = dx2; p.rdx2 = 1.f / dx2; p.dx4 = dx4; p.rdx4 = 1.f / dx4;
     switch (halo) {
     case 2: return launch_ks1d<2>(p, B, stream);
@@ -462,10 +488,25 @@ extern "C" int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, 
     return PPNN_E_SCHEME;
 }
 
-extern "C" int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, int endpoint, int nsteps,
-                             int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
-                             float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,
-                             void* stream) {
+extern "C" int ppnn_ks1d_rk4(const float* u, const float* source, float* u_out, int B, int n, int endpoint,
+                             int nsteps, int adv_accuracy, int d2_accuracy, int d4_accuracy,
+                             float dt, float dx, float dx2, float dx4, void* stream) {
+    return ks1d_entry(u, source, u_out, B, n, endpoint, nsteps, 0, adv_accuracy, d2_accuracy, d4_accuracy,
+                      dt, dx, dx2, dx4, stream);
+}
+
+extern "C" int ppnn_ks1d_rhs(const float* u, const float* source, float* f_out, int B, int n, int endpoint,
+                             int adv_accuracy, int d2_accuracy, int d4_accuracy,
+                             float dx, float dx2, float dx4, void* stream) {
+    if (u == f_out) return PPNN_E_MODE;
+    return ks1d_entry(u, source, f_out, B, n, endpoint, 0, 1, adv_accuracy, d2_accuracy, d4_accuracy,
+                      0.f, dx, dx2, dx4, stream);
+}
+
+static int ks2d_entry(const float* u, float* u_out, int B, int H, int W, int endpoint, int nsteps, int rhs_only,
+                      int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
+                      float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,
+                      void* stream) {
     if (!u || !u_out) return PPNN_E_NULL;
     if (B < 0 || nsteps < 0 || H < 2 || W < 2) return PPNN_E_SHAPE;
     Ks2dParams p;
@@ -475,7 +516,7 @@ extern "C" int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, 
     p.H = H; p.W = W; p.PH = endpoint ? H - 1 : H; p.PW = endpoint ? W - 1 : W;
     if (p.PH <= 2 * halo || p.PW <= 2 * halo) return PPNN_E_SHAPE;
     if (B == 0) return PPNN_OK;
-    p.u = u; p.out = u_out; p.nsteps = nsteps;
+    p.u = u; p.out = u_out; p.nsteps = nsteps; p.rhs_only = rhs_only;
     p.invW = 1.f / (float)W;
     p.c2 = c2; p.mixed = mixed_scale; p.dt = dt;
     p.dx = dx; p.rdx = 1.f / dx; p.dy = dy; p.rdy = 1.f / dy;
@@ -487,6 +528,22 @@ extern "C" int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, 
     case 4: return launch_ks2d<4>(p, B, stream);
     }
     return PPNN_E_SCHEME;
+}
+
+extern "C" int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, int endpoint, int nsteps,
+                             int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
+                             float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,
+                             void* stream) {
+    return ks2d_entry(u, u_out, B, H, W, endpoint, nsteps, 0, adv_accuracy, d2_accuracy, d4_accuracy, c2, mixed_scale,
+                      dt, dx, dy, dx2, dy2, dx4, dy4, stream);
+}
+
+extern "C" int ppnn_ks2d_rhs(const float* u, float* f_out, int B, int H, int W, int endpoint,
+                             int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
+                             float dx, float dy, float dx2, float dy2, float dx4, float dy4, void* stream) {
+    if (u == f_out) return PPNN_E_MODE;
+    return ks2d_entry(u, f_out, B, H, W, endpoint, 0, 1, adv_accuracy, d2_accuracy, d4_accuracy, c2, mixed_scale,
+                      0.f, dx, dy, dx2, dy2, dx4, dy4, stream);
 }
 
 extern "C" int ppnn_heat1d_pad(const float* u, const int* cls, const float* bv, float* out,

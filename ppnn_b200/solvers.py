@@ -70,6 +70,17 @@ class KS1D:
         return self.run(u, 1)
 
     @torch.no_grad()
+    def f(self, u: torch.Tensor) -> torch.Tensor:
+        """The right-hand side alone (the reference's ``f`` closure, ``operators.py:883-884``)."""
+        u, shape = _as_batch(u, 1)
+        B, n = u.shape[0], u.shape[-1]
+        out = torch.empty_like(u)
+        with L.on_device(u):
+            L.check(L.load().ppnn_ks1d_rhs(u.data_ptr(), L.ptr(self.source), out.data_ptr(), B, n, int(self.endpoint),
+                                           *self.acc, self.dx, self.dx2, self.dx4, L.stream()), "ppnn_ks1d_rhs")
+        return out.reshape(shape)
+
+    @torch.no_grad()
     def generate(self, u: torch.Tensor, nsteps: int, every: int = 500) -> torch.Tensor:
         """The loop of ``operators.py:899-907``: snapshot when ``i % every == 0`` (after step i) ->
         ``[B, T, ...]`` stacked on dim 1 like ``torch.stack(resultu, dim=1)``."""
@@ -161,6 +172,21 @@ class KS2D:
     def rk4(self, u: torch.Tensor) -> torch.Tensor:
         """One step (the reference's ``rk4`` closure, ``operators.py:805-815``)."""
         return self.run(u, 1)
+
+    @torch.no_grad()
+    def f(self, u: torch.Tensor) -> torch.Tensor:
+        """The right-hand side alone (the reference's ``f`` closure, ``operators.py:806-809``)."""
+        u, shape = _as_batch(u, 2)
+        B, H, W = u.shape[0], u.shape[-2], u.shape[-1]
+        out = torch.empty_like(u)
+        with L.on_device(u):
+            st = L.load().ppnn_ks2d_rhs(u.data_ptr(), out.data_ptr(), B, H, W, int(self.endpoint), *self.acc,
+                                        self.c2, self.mixed_scale, self.dx, self.dy, self.dx2, self.dy2,
+                                        self.dx4, self.dy4, L.stream())
+            if st == L.E_TOOBIG:
+                return self.f_composed(u.reshape(B, 1, H, W)).reshape(shape)
+            L.check(st, "ppnn_ks2d_rhs")
+        return out.reshape(shape)
 
 
 class HeatBC1D:

@@ -31,6 +31,8 @@ def test_ks2d_against_reference_golden(S):
     g = load_golden("solvers.npz")
     ks = S.KS2D(dt=1e-3, dx=PI8)
     u = g["ks2d/u0"].cuda()
+    # the right-hand side itself: with dt = 1e-3 a step moves u by ~1e-3 |f|, so parity of u alone would not pin f
+    assert_parity(ks.f(u).cpu(), g["ks2d/f0"], TOL, "ks2d f (fused kernel)")
     for i in range(3):                                   # one launch per step
         u = ks.rk4(u)
         assert_parity(u.cpu(), g[f"ks2d/u{i + 1}"], TOL, f"ks2d step {i + 1}")
@@ -55,7 +57,12 @@ def test_ks2d_sizes_against_oracle(S, h, w, endpoint, acc):
     kw = dict(adv_acc=acc[0], d2_acc=acc[1], d4_acc=acc[2], period_endpoint=endpoint)
     ref = O.ks2d_rk4_step(O.ks2d_rk4_step(u, 1e-3, PI8, **kw), 1e-3, PI8, **kw)
     ks = S.KS2D(dt=1e-3, dx=PI8, adv_accuracy=acc[0], d2_accuracy=acc[1], d4_accuracy=acc[2], endpoint=endpoint)
+    assert_parity(ks.f(u.cuda()).cpu(), O.ks2d_rhs(u, PI8, PI8, **kw), TOL, f"ks2d f {h}x{w}")
     assert_parity(ks.run(u.cuda(), 2).cpu(), ref, TOL, f"ks2d {h}x{w}")
+    # a step large enough for the increment to matter (a few times the production dt): pins the RK4 staging, not just u + O(dt)
+    big = 0.004
+    kb = S.KS2D(dt=big, dx=PI8, adv_accuracy=acc[0], d2_accuracy=acc[1], d4_accuracy=acc[2], endpoint=endpoint)
+    assert_parity(kb.rk4(u.cuda()).cpu(), O.ks2d_rk4_step(u, big, PI8, **kw), TOL, f"ks2d {h}x{w}, dt={big}")
 
 
 def test_ks2d_oversize_mesh_composes_tier_a(S):
@@ -74,6 +81,8 @@ def test_ks1d_against_reference_golden(S):
     g = load_golden("solvers.npz")
     ks = S.KS1D(dt=1e-4, dx=PI8, source=g["ks1d/source"].cuda())
     u = g["ks1d/u0"].cuda()
+    assert_parity(ks.f(u).cpu(), g["ks1d/f0"], TOL, "ks1d f (fused kernel)")
+    assert_parity(S.KS1D(dt=1e-4, dx=PI8).f(u).cpu(), g["ks1d/rhs_ks1d"], TOL, "ks1d f without source = rhs.ks1d")
     for i in range(3):
         u = ks.rk4(u)
         assert_parity(u.cpu(), g[f"ks1d/u{i + 1}"], TOL, f"ks1d step {i + 1}")
@@ -103,12 +112,18 @@ def test_ks1d_sizes_against_oracle(S, n, endpoint, acc):
             return (-O.stencil1d(pad(w, 4), "Central", 8) / PI8 ** 2 - O.stencil1d(pad(w, 4), "Central_4th", 6) / PI8 ** 4
                     - 0.5 * O.stencil1d(pad(w * w, 3), "Upwind", 3) / PI8 + src)
         ref = O.rk4_step(f, O.rk4_step(f, u, 1e-4), 1e-4)
+        fref, big_ref = f(u), O.rk4_step(f, u, 0.003)
     else:
         kw = dict(adv_acc=acc[0], d2_acc=acc[1], d4_acc=acc[2], period_endpoint=endpoint)
         ref = O.ks1d_rk4_step(O.ks1d_rk4_step(u, 1e-4, PI8, src, **kw), 1e-4, PI8, src, **kw)
+        fref, big_ref = O.ks1d_rhs(u, PI8, src, **kw), O.ks1d_rk4_step(u, 0.003, PI8, src, **kw)
     ks = S.KS1D(dt=1e-4, dx=PI8, source=src.cuda(), adv_accuracy=acc[0], d2_accuracy=acc[1], d4_accuracy=acc[2],
                 endpoint=endpoint)
+    assert_parity(ks.f(u.cuda()).cpu(), fref, TOL, f"ks1d f n={n}")
     assert_parity(ks.run(u.cuda(), 2).cpu(), ref, TOL, f"ks1d n={n}")
+    kb = S.KS1D(dt=0.003, dx=PI8, source=src.cuda(), adv_accuracy=acc[0], d2_accuracy=acc[1], d4_accuracy=acc[2],
+                endpoint=endpoint)
+    assert_parity(kb.rk4(u.cuda()).cpu(), big_ref, TOL, f"ks1d n={n}, dt=0.003")
 
 
 def test_ks_batch_independence_and_generate(S):

@@ -240,7 +240,7 @@ def workload_config(B, n):
 # ----------------------------------------------------------------------------- config 5: roofline sweep
 def cpu_sweep_fn():
     """CPU-reference column of the sweep: the staged reference's own operator / rhs objects (oracle/_ref) on the
-    host cores, per (op, N) on a bounded batch (>= 4 M grid points, at least one sample), G units/s."""
+    host cores, per (op, N) on a bounded sample (about 4 M grid points), G units/s."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_closures as R
@@ -260,10 +260,13 @@ def cpu_sweep_fn():
         return torch.cat((w[:, :, :, -h:], w, w[:, :, :, :h]), dim=3)
 
     def cpu(name, N):
+        # bounded sample: B samples of N x N while they stay under 4 M grid points, else a strip of Hc rows x N columns
+        # of one sample (every op is local, so the cost per point is that of the full mesh)
         B = max(1, (1 << 22) // (N * N))
+        Hc = N if N * N <= (1 << 22) else max(64, (1 << 22) // N)
         g = torch.Generator().manual_seed(1)
-        u = torch.rand(B, 1, N, N, generator=g) - 0.4
-        v = torch.rand(B, 1, N, N, generator=g) - 0.4
+        u = torch.rand(B, 1, Hc, N, generator=g) - 0.4
+        v = torch.rand(B, 1, Hc, N, generator=g) - 0.4
         mu = torch.full((B, 1, 1, 1), 0.04)
         dx = 0.0125
         ux, uy, ux1, uy1 = padx(u, 3), pady(u, 3), padx(u, 1), pady(u, 1)
@@ -288,7 +291,7 @@ def cpu_sweep_fn():
                 fn()
                 reps += 1
             dt = (time.perf_counter() - t0) / reps
-        return units * B * N * N / dt / 1e9, cores
+        return units * B * Hc * N / dt / 1e9, cores
     return cpu
 
 
@@ -327,7 +330,7 @@ def run_sweep(args):
               f"`bench.py --sweep {args.sweep} --gpus {world}`: fp32, CUDA events, max over ranks, 6-20 repetitions after 3 "
               f"warm-ups; N x N periodic grids x GLOBAL batch B sharded over the GPUs (cells with B < GPUs skipped).  "
               f"CPU reference = the reference's own operator / rhs modules (oracle/_ref) on the host's "
-              f"{os.cpu_count()} hardware threads, per (op, N) on a bounded batch (>= 4 M grid points); units = output "
+              f"{os.cpu_count()} hardware threads, per (op, N) on a bounded sample (about 4 M grid points: whole samples, or a strip of rows of one sample at 4096^2 and beyond); units = output "
               f"points (operators, rhs) or point-updates (step).\n", flush=True)
     SW.sweep(dev, world, rank, quick=args.sweep == "quick", cpu=cpu, barrier=barrier, max_over_ranks=max_over_ranks)
     if world > 1:
@@ -415,7 +418,7 @@ def train_leg(torch, dist, dev, world, rank, local, timed, L):
     return out
 
 
-def datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier):
+def datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier, link=None):
     """BASELINE configs[3]: the fine-grid Burgers generator (operators.py:403-492) at the reference's LENGTH
     (20 001 steps, snapshot every 200 => 101 snapshots), 1025^2 (the reference's duplicated-endpoint convention at
     config 4's resolution), 8 viscosities x 8 initial conditions = 64 samples PER GPU, sharded with no communication.
@@ -438,6 +441,17 @@ def datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier):
                     "gpoint_updates_per_s": P * 2 * 1025 * 1025 * 20001 / sec / 1e9,
                     "snapshot_gb_per_gpu": 101 * 64 * 2 * 1025 * 1025 * 4 / 1e9, "finite": finite}
         torch.cuda.empty_cache()
+    if link:
+        # the host sink moves every snapshot over the host link while the solver runs: its floor is the slower of the
+        # solver alone (the device-sink solve time is an upper bound of it) and the D2H at the measured link rate
+        h = out["host_sink_discard"]
+        gb = h["snapshot_gb_per_gpu"]
+        h["d2h_gbs_per_gpu"] = gb / h["solve_seconds"]
+        h["d2h_ceiling_gbs_per_gpu"] = link["d2h_gbs_per_gpu"]
+        link_floor = gb / link["d2h_gbs_per_gpu"]
+        h["link_floor_seconds"] = link_floor
+        h["bound"] = "host link (D2H)" if link_floor > 0.9 * out["device_sink"]["solve_seconds"] else "solver (the D2H is hidden behind it)"
+        h["frac_of_floor"] = max(link_floor, min(out["device_sink"]["solve_seconds"], h["solve_seconds"])) / h["solve_seconds"]
     out["note"] = ("device_sink: the 101 snapshots stay in HBM (54 GB per GPU; the form PdeDataset trains from); "
                    "host_sink_discard: every snapshot is copied to pinned host memory on a side stream and dropped "
                    "(the box cannot hold 8 x 54 GB): solver + the D2H the reference does at operators.py:479-482")
@@ -543,11 +557,12 @@ def run_ours(args):
             cur.wait_stream(s1); cur.wait_stream(s2)
         res = {}
         for tag, h2d, d2h in (("h2d", True, False), ("d2h", False, True), ("bidir", True, True)):
-            t = timed(lambda: run(h2d, d2h), 2, 1)          # ms per run of `reps` copies each way, max over ranks
+            # ms per run of `reps` copies each way, max over ranks; best of 3 trials (a ceiling, so the fastest counts)
+            t = min(timed(lambda: run(h2d, d2h), 2, 1) for _ in range(3))
             res[tag + "_gbs_per_gpu"] = reps * nbytes / t / 1e6
         res["aggregate_bidir_gbs"] = world * 2 * res["bidir_gbs_per_gpu"]
         res["how"] = ("256 MB pinned<->device copies, 6 back to back per direction, all ranks at once, CUDA events, max over "
-                      "ranks; bidir = H2D and D2H streams together, per-direction rate")
+                      "ranks, best of 3 trials; bidir = H2D and D2H streams together, per-direction rate")
         return res
     link = link_ceiling()
 
@@ -658,12 +673,39 @@ def run_ours(args):
                                                              "hbm_gbs": 8 * fpts / t / 1e6}
         del fu, a, b_, a2, b2
 
+        # small explicit solvers with the state on chip: all steps in ONE launch
+        try:
+            import math
+            from ppnn_b200 import KS1D, KS2D, HeatBC1D
+            xs = torch.linspace(0, 8 * math.pi, 129, device=dev).reshape(1, 1, -1)
+            ku = torch.cos(xs / 16 + torch.randn(256, 1, 1, device=dev)) * (1 + torch.sin(xs / 16 + torch.randn(256, 1, 1, device=dev)))
+            ks1 = KS1D(dt=1e-4, dx=math.pi / 8, source=0.1 * torch.exp(-(xs - 4 * math.pi) ** 2 / 2))
+            t = timed(lambda: ks1.run(ku, 20000), 2, 1)
+            extras["ks1d_rk4_256x129"] = {"us_per_step": t * 1e3 / 20000, "steps_per_launch": 20000,
+                                          "gpts": world * 256 * 129 * 20000 / t / 1e6}
+            x2 = torch.linspace(0, 8 * math.pi, 65, device=dev)
+            kw = (torch.cos(x2.reshape(-1, 1) / 4) * (1 + torch.sin(x2.reshape(1, -1) / 4))).reshape(1, 1, 65, 65)
+            kw = (kw * torch.linspace(0.9, 1.1, 296, device=dev).reshape(-1, 1, 1, 1)).contiguous()
+            ks2 = KS2D(dt=1e-3, dx=math.pi / 8)
+            t = timed(lambda: ks2.run(kw, 1000), 2, 1)
+            extras["ks2d_rk4_296x65x65"] = {"us_per_step": t * 1e3 / 1000, "steps_per_launch": 1000,
+                                            "gpts": world * 296 * 65 * 65 * 1000 / t / 1e6}
+            hb = torch.randn(256, 1, 126, device=dev).cumsum(-1) * 0.1
+            hc, hv = torch.randint(0, 2, (256, 1, 2), device=dev), torch.rand(256, 1, 2, device=dev) * 2 - 1
+            heat = HeatBC1D(0.01, 16 * math.pi / 127)
+            t = timed(lambda: heat.generate(hb, hc, hv, 10001, 50), 2, 1)
+            extras["bv_heat_256x126_10001steps"] = {"us_per_step": t * 1e3 / 10001, "launches": 201,
+                                                    "gpts": world * 256 * 126 * 10001 / t / 1e6}
+            del ku, kw, hb
+        except Exception as exc:
+            extras["onchip_solvers_error"] = repr(exc)[:300]
+
         try:
             extras["train_unrolled_burgers_fPDE"] = train_leg(torch, dist, dev, world, rank, local, timed, L)
         except Exception as exc:
             extras["train_unrolled_error"] = repr(exc)[:300]
         try:
-            extras["datagen_1025x64_per_gpu"] = datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier)
+            extras["datagen_1025x64_per_gpu"] = datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier, link)
         except Exception as exc:
             extras["datagen_error"] = repr(exc)[:300]
 

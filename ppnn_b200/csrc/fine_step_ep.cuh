@@ -226,7 +226,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
                     const float2 c = xu[HL];
                     const float2 vcen = make_float2(vr[0], 0.f);
                     float2 unew, vnew;
-                    fine_point_update<HL, MODE>(p, mu, c, vcen, xu, xv, yu, yv, unew, vnew);
+                    fine_point_update<HL, MODE, true>(p, mu, c, vcen, xu, xv, yu, yv, unew, vnew);
                     if (r0 + n * R + q < r1) { ou[(size_t)q * W] = unew.x; ov[(size_t)q * W] = vnew.x; }
                 }
                 __syncwarp();
@@ -299,7 +299,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
                 const float2 c = wu[HL + q];
                 const float2 vcen = VWIN ? wv[HL + q] : make_float2(vr[0], vr[dB]);
                 float2 unew, vnew;
-                fine_point_update<HL, MODE>(p, mu, c, vcen, wu + q, wv + (VWIN ? q : 0), yu, yv, unew, vnew);
+                fine_point_update<HL, MODE, true>(p, mu, c, vcen, wu + q, wv + (VWIN ? q : 0), yu, yv, unew, vnew);
                 if (active && r0 + n * R + q < r1) {
                     ouA[(size_t)q * W] = unew.x; ovA[(size_t)q * W] = vnew.x;
                     if (hasB) { ouA[(size_t)q * W + dB] = unew.y; ovA[(size_t)q * W + dB] = vnew.y; }

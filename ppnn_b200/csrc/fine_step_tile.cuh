@@ -36,7 +36,9 @@ struct FineTilePlan {
 
 // One explicit update of a packed pair of grid points from its x-direction windows (xu, xv: 2*HL+1
 // rows centred on the point) and y-direction windows (yu, yv).
-template <int HL, int MODE>
+// UNI: take the warp-uniform upwind fast path (it pays in the instruction-bound endpoint kernel, not in the
+// memory-bound tile kernel)
+template <int HL, int MODE, bool UNI = false>
 __device__ __forceinline__ void fine_point_update(const FineParams& p, float mu, float2 c, float2 vcen,
                                                   const float2* xu, const float2* xv, const float2* yu, const float2* yv,
                                                   float2& unew, float2& vnew) {
@@ -62,7 +64,9 @@ __device__ __forceinline__ void fine_point_update(const FineParams& p, float mu,
         vnew = fma2(p.dt, rv, vcen);
     } else {
         // burgers2Dpu then burgers2Dpv with the updated u (operators.py:474-475)
-        const float2 dxu = upwind2<HL>(p, c, xu), dyu = upwind2<HL>(p, c, yu);
+        float2 dxu, dyu;
+        if (UNI && MODE == FINE_AS_WRITTEN) upwind2_xy<HL>(p, c, xu, yu, dxu, dyu);
+        else { dxu = upwind2<HL>(p, c, xu); dyu = upwind2<HL>(p, c, yu); }
         const float2 lapu = mul2(f2(mu), add2(mul2(central2<HL>(p, xu), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
         const float2 advy = neg2(mul2(mul2(vcen, dyu), f2(p.rdy)));
         unew = fma2(p.dt, add2(add2(mul2(mul2(neg2(c), dxu), f2(p.rdx)), advy), lapu), c);

@@ -10,6 +10,8 @@ b = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 mode = sys.argv[3] if len(sys.argv) > 3 else "as_written"
 dev = torch.device("cuda")
 f = bench.synth_fields(b, n, dev, 5)
+if len(sys.argv) > 4 and sys.argv[4] == "pos":      # all-positive fields like the reference's initial conditions
+    f = f + 0.6
 u, v = f[:, 0].contiguous(), f[:, 1].contiguous()
 u2, v2 = torch.empty_like(u), torch.empty_like(v)
 mu = torch.full((b,), 0.04, device=dev)
@@ -27,4 +29,4 @@ e.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(e) / reps
 pts = b * 2 * n * n
-print(f"fine {mode} N={n} B={b}: {ms:.4f} ms/step, {pts / ms / 1e6:.1f} Gpt/s, {8 * pts / ms / 1e6:.0f} GB/s")
+print(f"[{os.path.basename(os.environ.get('PPNN_B200_LIB', 'libppnn_b200.so'))}] fine {mode} {'pos' if len(sys.argv) > 4 else 'mixed'} N={n} B={b}: {ms:.4f} ms/step, {pts / ms / 1e6:.1f} Gpt/s, {8 * pts / ms / 1e6:.0f} GB/s")

@@ -263,8 +263,9 @@ int ppnn_ks1d_rhs(const float* u, const float* source, float* f_out, int B, int 
  *          - 0.5*dudx(pad(u*u))/dx - 0.5*dudy(pad(u*u))/dy
  * (reference: c2 = 0.1, mixed_scale = 1: the mixed term is NOT divided by dx2*dy2 there), Central2 /
  * Central4 / Upwind1 stencils, every pad the duplicated-endpoint wrap of operators.py:761-765.
- * u, u_out [B, H, W]; 4*H*W floats must fit in shared memory (H*W <= 14528, e.g. 120^2), else
- * PPNN_E_TOOBIG: compose the step from the Tier-A operators.  u_out may alias u.             */
+ * u, u_out [B, H, W]; four frames of (H+2h) x (W+2h) floats (h = the widest stencil's halo) must fit in
+ * shared memory ((H+2h)*(W+2h) <= 14528, e.g. 114^2 at h = 3), else PPNN_E_TOOBIG: compose the step from
+ * the Tier-A operators.  u_out may alias u.                                                   */
 int ppnn_ks2d_rk4(const float* u, float* u_out, int B, int H, int W, int endpoint, int nsteps,
                   int adv_accuracy, int d2_accuracy, int d4_accuracy, float c2, float mixed_scale,
                   float dt, float dx, float dy, float dx2, float dy2, float dx4, float dy4,

@@ -160,38 +160,48 @@ struct Ks2dParams {
     const float* u; float* out;
     int H, W, PH, PW, nsteps;
     int rhs_only;        // write f(u) instead of stepping (the reference's `f` closure)
-    float invW;
+    int FH, FW;          // padded frame: (H + 2*HALO) x (W + 2*HALO)
+    float invW, invFW;
     float c2, mixed, dt;
     float dx, rdx, dy, rdy, dx2, rdx2, dy2, rdy2, dx4, rdx4, dy4, rdy4;
     CenteredTaps d2, d4, af, ab;
 };
 
-// phase A: second-derivative fields of the stage input (their wrapped second derivatives across the other axis
-// give the mixed term - d2udy2(padbcy(d2udx2(padbcx(u)))) - d2udx2(padbcx(d2udy2(padbcy(u)))), operators.py:808)
-template <int HALO, bool WRAP>
-__device__ __forceinline__ void ks2d_second(const Ks2dParams& p, const float* __restrict__ s, int i, int j,
-                                            float* lx, float* ly) {
-    float ax = 0.f, ay = 0.f;
+// The stage vector lives in shared memory as a PADDED FRAME: HALO ghost rows / columns around the H x W points hold
+// the periodic images the reference's pads create (operators.py:761-765), so every stencil reads linearly -- no wrap
+// arithmetic and, more important on a 65-point row, no warp that has to run both a wrapped and an interior code path.
+// The ghosts cost no extra pass: the thread that produces a point near an edge also stores its periodic image(s).
+//
+// phase A: second-derivative fields of the stage input, LX = d2/dx2 on rows [0,H) x frame columns and LY = d2/dy2 on
+// frame rows x columns [0,W) (their ghosts are evaluated directly, from the ghosts of S); their second derivatives
+// across the other axis are the mixed term - d2udy2(padbcy(d2udx2(padbcx(u)))) - d2udx2(padbcx(d2udy2(padbcy(u)))),
+// operators.py:808.
+template <int HALO>
+__device__ __forceinline__ void ks2d_second(const Ks2dParams& p, const float* __restrict__ s, float* __restrict__ LX,
+                                            float* __restrict__ LY, int cell, int fi, int fj) {
+    const bool rowok = fi >= HALO && fi < p.H + HALO, colok = fj >= HALO && fj < p.W + HALO;
+    if (rowok) {
+        float ax = 0.f;
 #pragma unroll
-    for (int d = -HALO; d <= HALO; ++d) {
-        const int ii = WRAP ? wrap_axis(i + d, p.H, p.PH) : i + d;
-        const int jj = WRAP ? wrap_axis(j + d, p.W, p.PW) : j + d;
-        ax = fmaf(p.d2.c[d + HALO], s[ii * p.W + j], ax);
-        ay = fmaf(p.d2.c[d + HALO], s[i * p.W + jj], ay);
+        for (int d = -HALO; d <= HALO; ++d) ax = fmaf(p.d2.c[d + HALO], s[cell + d * p.FW], ax);
+        LX[cell] = ax;
     }
-    *lx = ax;
-    *ly = ay;
+    if (colok) {
+        float ay = 0.f;
+#pragma unroll
+        for (int d = -HALO; d <= HALO; ++d) ay = fmaf(p.d2.c[d + HALO], s[cell + d], ay);
+        LY[cell] = ay;
+    }
 }
 
-template <int HALO, bool WRAP>
+// phase B: f at interior point `cell` of the frame
+template <int HALO>
 __device__ __forceinline__ float ks2d_rhs(const Ks2dParams& p, const float* __restrict__ s,
-                                          const float* __restrict__ LX, const float* __restrict__ LY, int i, int j) {
+                                          const float* __restrict__ LX, const float* __restrict__ LY, int cell) {
     float d4x = 0.f, d4y = 0.f, fx = 0.f, bx = 0.f, fy = 0.f, by = 0.f, mxy = 0.f, myx = 0.f;
 #pragma unroll
     for (int d = -HALO; d <= HALO; ++d) {
-        const int ii = WRAP ? wrap_axis(i + d, p.H, p.PH) : i + d;
-        const int jj = WRAP ? wrap_axis(j + d, p.W, p.PW) : j + d;
-        const int ox = ii * p.W + j, oy = i * p.W + jj;
+        const int ox = cell + d * p.FW, oy = cell + d;
         const float sx = s[ox], sy = s[oy];
         d4x = fmaf(p.d4.c[d + HALO], sx, d4x);
         d4y = fmaf(p.d4.c[d + HALO], sy, d4y);
@@ -203,13 +213,13 @@ __device__ __forceinline__ float ks2d_rhs(const Ks2dParams& p, const float* __re
         mxy = fmaf(p.d2.c[d + HALO], LX[oy], mxy);      // d2/dy2 of the d2/dx2 field
         myx = fmaf(p.d2.c[d + HALO], LY[ox], myx);      // d2/dx2 of the d2/dy2 field
     }
-    const int o = i * p.W + j;
-    const float c = s[o] * s[o];
+    const float c = s[cell] * s[cell];
+    // (u_int <= 0) * forward + (u_int > 0) * backward on the differentiated field u*u (operators.py:257-258)
     const float advx = (c <= 0.f ? fx : 0.f) + (c > 0.f ? bx : 0.f);
     const float advy = (c <= 0.f ? fy : 0.f) + (c > 0.f ? by : 0.f);
     // - c2*Lx/dx2 - c2*Ly/dy2 - D4x/dx4 - D4y/dy4 - Lyy(Lx) - Lxx(Ly) - 0.5*d(u^2)/dx /dx - 0.5*d(u^2)/dy /dy
-    float r = -div_by(p.c2 * LX[o], p.dx2, p.rdx2);
-    r -= div_by(p.c2 * LY[o], p.dy2, p.rdy2);
+    float r = -div_by(p.c2 * LX[cell], p.dx2, p.rdx2);
+    r -= div_by(p.c2 * LY[cell], p.dy2, p.rdy2);
     r -= div_by(d4x, p.dx4, p.rdx4);
     r -= div_by(d4y, p.dy4, p.rdy4);
     r -= p.mixed * mxy;
@@ -219,6 +229,24 @@ __device__ __forceinline__ float ks2d_rhs(const Ks2dParams& p, const float* __re
     return r;
 }
 
+// store a stage value at its point and at the periodic images of that point inside the ghost frame: along an axis of
+// n points and period P the image below the first point is j - P when j in [P-HALO, P), the one above the last is
+// j + P when j in [n-P, n-P+HALO)  (duplicated endpoint, P = n-1: u[P-3..P-1] | u | u[1..3], operators.py:761-765)
+template <int HALO>
+__device__ __forceinline__ void ks2d_store(const Ks2dParams& p, float* __restrict__ s, int i, int j, float v) {
+    const int base = (i + HALO) * p.FW + (j + HALO);
+    int dj = 0, di = 0;
+    if (j >= p.PW - HALO && j < p.PW) dj = -p.PW; else if (j >= p.W - p.PW && j < p.W - p.PW + HALO) dj = p.PW;
+    if (i >= p.PH - HALO && i < p.PH) di = -p.PH; else if (i >= p.H - p.PH && i < p.H - p.PH + HALO) di = p.PH;
+    s[base] = v;
+    if (dj) s[base + dj] = v;
+    if (di) {
+        s[base + di * p.FW] = v;
+        if (dj) s[base + di * p.FW + dj] = v;
+    }
+    // a point can sit in BOTH image ranges of an axis only when the period is shorter than 2*HALO: rejected on the host
+}
+
 // threads per CTA: 1024 (64 registers) while a thread owns <= 2 points, 640 (96 registers) beyond
 constexpr int ks2d_max_threads(int pts) { return pts <= 2 ? 1024 : 640; }
 
@@ -226,11 +254,11 @@ template <int HALO, int PTS>
 __global__ void __launch_bounds__(ks2d_max_threads(PTS))
 ks2d_rk4_kernel(const Ks2dParams p) {
     extern __shared__ float sm[];
-    const int N = p.H * p.W;
+    const int N = p.H * p.W, NF = p.FH * p.FW;
     float* cur = sm;
-    float* nxt = sm + N;
-    float* LX = sm + 2 * N;
-    float* LY = sm + 3 * N;
+    float* nxt = sm + NF;
+    float* LX = sm + 2 * NF;
+    float* LY = sm + 3 * NF;
     const int T = blockDim.x;
     const float* uin = p.u + (size_t)blockIdx.x * N;
     float U[PTS], A[PTS];
@@ -238,39 +266,35 @@ ks2d_rk4_kernel(const Ks2dParams p) {
     for (int q = 0; q < PTS; ++q) {
         const int idx = threadIdx.x + q * T;
         U[q] = 0.f; A[q] = 0.f;
-        if (idx < N) { U[q] = uin[idx]; cur[idx] = U[q]; }
+        if (idx < N) {
+            const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
+            U[q] = uin[idx];
+            ks2d_store<HALO>(p, cur, i, j, U[q]);
+        }
     }
     __syncthreads();
     if (p.rhs_only) {
 #pragma unroll 1
-        for (int idx = threadIdx.x; idx < N; idx += T) {
-            const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
-            ks2d_second<HALO, true>(p, cur, i, j, LX + idx, LY + idx);
+        for (int cell = threadIdx.x; cell < NF; cell += T) {
+            const int fi = __float2int_rd(((float)cell + 0.5f) * p.invFW), fj = cell - fi * p.FW;
+            ks2d_second<HALO>(p, cur, LX, LY, cell, fi, fj);
         }
         __syncthreads();
         float* o = p.out + (size_t)blockIdx.x * N;
 #pragma unroll 1
         for (int idx = threadIdx.x; idx < N; idx += T) {
             const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
-            o[idx] = ks2d_rhs<HALO, true>(p, cur, LX, LY, i, j);
+            o[idx] = ks2d_rhs<HALO>(p, cur, LX, LY, (i + HALO) * p.FW + j + HALO);
         }
         return;
     }
     for (int step = 0; step < p.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
-#pragma unroll
-            for (int q = 0; q < PTS; ++q) {
-                const int idx = threadIdx.x + q * T;
-                if (idx < N) {
-                    const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
-                    const bool inner = i >= HALO && i < p.H - HALO && j >= HALO && j < p.W - HALO;
-                    float lx, ly;
-                    if (inner) ks2d_second<HALO, false>(p, cur, i, j, &lx, &ly);
-                    else       ks2d_second<HALO, true>(p, cur, i, j, &lx, &ly);
-                    LX[idx] = lx;
-                    LY[idx] = ly;
-                }
+#pragma unroll 2
+            for (int cell = threadIdx.x; cell < NF; cell += T) {
+                const int fi = __float2int_rd(((float)cell + 0.5f) * p.invFW), fj = cell - fi * p.FW;
+                ks2d_second<HALO>(p, cur, LX, LY, cell, fi, fj);
             }
             __syncthreads();
 #pragma unroll
@@ -278,10 +302,8 @@ ks2d_rk4_kernel(const Ks2dParams p) {
                 const int idx = threadIdx.x + q * T;
                 if (idx < N) {
                     const int i = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - i * p.W;
-                    const bool inner = i >= HALO && i < p.H - HALO && j >= HALO && j < p.W - HALO;
-                    const float k = inner ? ks2d_rhs<HALO, false>(p, cur, LX, LY, i, j)
-                                          : ks2d_rhs<HALO, true>(p, cur, LX, LY, i, j);
-                    nxt[idx] = rk4_advance(stage, k, U[q], A[q], p.dt);
+                    const float k = ks2d_rhs<HALO>(p, cur, LX, LY, (i + HALO) * p.FW + j + HALO);
+                    ks2d_store<HALO>(p, nxt, i, j, rk4_advance(stage, k, U[q], A[q], p.dt));
                 }
             }
             __syncthreads();
@@ -310,9 +332,11 @@ static int launch_ks2d_pts(const Ks2dParams& p, int B, size_t smem, void* stream
 }
 
 template <int HALO>
-static int launch_ks2d(const Ks2dParams& p, int B, void* stream) {
+static int launch_ks2d(Ks2dParams& p, int B, void* stream) {
     const int N = p.H * p.W;
-    const size_t smem = (size_t)4 * N * sizeof(float);
+    p.FH = p.H + 2 * HALO; p.FW = p.W + 2 * HALO;
+    p.invFW = 1.f / (float)p.FW;
+    const size_t smem = (size_t)4 * p.FH * p.FW * sizeof(float);
     if (smem > 227 * 1024) return PPNN_E_TOOBIG;
     auto fits = [N](int pts) { return (N + pts - 1) / pts <= ks2d_max_threads(pts); };
     if (fits(1)) return launch_ks2d_pts<HALO, 1>(p, B, smem, stream);

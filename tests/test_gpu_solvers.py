@@ -46,7 +46,7 @@ def test_ks2d_against_reference_golden(S):
 
 
 @pytest.mark.parametrize("h,w,endpoint,acc", [(64, 64, False, (3, 6, 4)), (33, 47, True, (3, 6, 4)), (40, 40, True, (2, 4, 2)),
-                                              (97, 97, True, (3, 6, 4)), (120, 121, True, (3, 6, 4)), (31, 30, False, (2, 4, 2))])
+                                              (97, 97, True, (3, 6, 4)), (114, 113, True, (3, 6, 4)), (31, 30, False, (2, 4, 2))])
 def test_ks2d_sizes_against_oracle(S, h, w, endpoint, acc):
     """every points-per-thread instantiation (1 .. 24), both periodic conventions, both stencil families"""
     torch.manual_seed(h * 1000 + w)

@@ -73,23 +73,22 @@ __device__ __forceinline__ float2 upwind2(const FineParams& p, float2 c, const f
     return make_float2(sel1(c.x, f.x, b.x), sel1(c.y, f.y, b.y));
 }
 
-// The same for the x- and the y-derivative of one field (one switch: both look at the centre value `c`).  When every
-// lane of the warp sees a positive centre in both packed rows -- always on the reference's data, whose initial
-// conditions are normalised to [0.1, 1.1] (operators.py:436-445) -- only the backward stencil is evaluated: half
-// the FFMA2s and no selects.  Same values as the general path (the unselected branch never contributes).
+// backward-biased stencil alone: what upwind2 returns where the centre value is positive
 template <int HL>
-__device__ __forceinline__ void upwind2_xy(const FineParams& p, float2 c, const float2* xw, const float2* yw,
-                                           float2& dx, float2& dy) {
-    const bool pos = c.x > 0.f && c.y > 0.f;
-    if (__all_sync(__activemask(), pos)) {
-        float2 bx = f2(0.f), by = f2(0.f);
+__device__ __forceinline__ float2 upwind2_bwd(const FineParams& p, const float2* w /* centre at HL */) {
+    float2 b = f2(0.f);
 #pragma unroll
-        for (int k = 0; k <= HL; ++k) { bx = fma2(p.ab[k], xw[k], bx); by = fma2(p.ab[k], yw[k], by); }
-        dx = bx; dy = by;
-    } else {
-        dx = upwind2<HL>(p, c, xw);
-        dy = upwind2<HL>(p, c, yw);
-    }
+    for (int k = 0; k <= HL; ++k) b = fma2(p.ab[k], w[k], b);
+    return b;
+}
+
+// Warp-uniform test for the upwind fast path: every lane sees positive centres in both packed rows (of u, and of v
+// when v's derivatives are needed).  Always true on the reference's data, whose initial conditions are normalised to
+// [0.1, 1.1] (operators.py:436-445): then only the backward stencils are evaluated -- half the FFMA2s of the upwind
+// part and no selects.  Same values as the general path (the unselected branch never contributes).
+__device__ __forceinline__ bool all_positive(float2 c, float2 v, bool with_v) {
+    const bool pos = c.x > 0.f && c.y > 0.f && (!with_v || (v.x > 0.f && v.y > 0.f));
+    return __all_sync(__activemask(), pos);
 }
 
 template <int HL>

@@ -64,17 +64,22 @@ __device__ __forceinline__ void fine_point_update(const FineParams& p, float mu,
         vnew = fma2(p.dt, rv, vcen);
     } else {
         // burgers2Dpu then burgers2Dpv with the updated u (operators.py:474-475)
-        float2 dxu, dyu;
-        if (UNI && MODE == FINE_AS_WRITTEN) upwind2_xy<HL>(p, c, xu, yu, dxu, dyu);
-        else { dxu = upwind2<HL>(p, c, xu); dyu = upwind2<HL>(p, c, yu); }
+        constexpr bool VDER = MODE != FINE_AS_WRITTEN;          // quirk Q3: as written, v re-uses u's derivative fields
+        float2 dxu, dyu, dxv = f2(0.f), dyv = f2(0.f);
+        // (the fast path is taken in as-written mode only: with v's windows live as well the two code paths cost
+        //  the intended-mode kernel its registers -- 0.285 -> 0.41 ms at 64 x 1025^2 when tried)
+        if (UNI && !VDER && all_positive(c, vcen, false)) {
+            dxu = upwind2_bwd<HL>(p, xu); dyu = upwind2_bwd<HL>(p, yu);
+        } else {
+            dxu = upwind2<HL>(p, c, xu); dyu = upwind2<HL>(p, c, yu);
+            if (VDER) { dxv = upwind2<HL>(p, vcen, xv); dyv = upwind2<HL>(p, vcen, yv); }
+        }
         const float2 lapu = mul2(f2(mu), add2(mul2(central2<HL>(p, xu), f2(p.rdx2)), mul2(central2<HL>(p, yu), f2(p.rdy2))));
         const float2 advy = neg2(mul2(mul2(vcen, dyu), f2(p.rdy)));
         unew = fma2(p.dt, add2(add2(mul2(mul2(neg2(c), dxu), f2(p.rdx)), advy), lapu), c);
-        if (MODE == FINE_AS_WRITTEN) {
-            // quirk Q3: v is advected and diffused with u's derivative fields
+        if (!VDER) {
             vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxu), f2(p.rdx)), advy), lapu), vcen);
         } else {
-            const float2 dxv = upwind2<HL>(p, vcen, xv), dyv = upwind2<HL>(p, vcen, yv);
             const float2 lapv = mul2(f2(mu), add2(mul2(central2<HL>(p, xv), f2(p.rdx2)), mul2(central2<HL>(p, yv), f2(p.rdy2))));
             vnew = fma2(p.dt, add2(add2(mul2(mul2(neg2(unew), dxv), f2(p.rdx)),
                                         neg2(mul2(mul2(vcen, dyv), f2(p.rdy)))), lapv), vcen);

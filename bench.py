@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="samples per GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel timings")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-legs", action="store_true", help="extras: kernels only (no training / datagen / rollout legs); for ncu runs")
     ap.add_argument("--cpu-batch", type=int, default=240)
     ap.add_argument("--sweep", nargs="?", const="full", choices=["quick", "full"],
                     help="BASELINE configs[4]: stencil roofline sweep (markdown table on stdout) instead of the bench line")
@@ -706,17 +707,21 @@ def run_ours(args):
             extras["onchip_solvers_error"] = repr(exc)[:300]
 
         try:
-            extras["train_unrolled_burgers_fPDE"] = train_leg(torch, dist, dev, world, rank, local, timed, L)
+            if not args.no_legs:
+                extras["train_unrolled_burgers_fPDE"] = train_leg(torch, dist, dev, world, rank, local, timed, L)
         except Exception as exc:
             extras["train_unrolled_error"] = repr(exc)[:300]
         try:
-            extras["datagen_1025x64_per_gpu"] = datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier, link)
+            if not args.no_legs:
+                extras["datagen_1025x64_per_gpu"] = datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier, link)
         except Exception as exc:
             extras["datagen_error"] = repr(exc)[:300]
 
         # rollout (train2D.py:230-245): K1 -> network -> K2 per step, CUDA-graph replayed,
         # around a random-weight network with the layer shapes of cnn2dRich (ppnn_b200/nets.py)
         try:
+            if args.no_legs:
+                raise StopIteration
             from ppnn_b200.nets import ConvResNet
             torch.manual_seed(1)
             net = ConvResNet(True).to(dev).eval()
@@ -744,6 +749,8 @@ def run_ours(args):
                                        "fp32/cudnn) + K2 + snapshot copy per step"}
                 del plan
                 del res
+        except StopIteration:
+            pass
         except Exception as exc:   # the rollout extra must never take the headline down
             extras["rollout_error"] = repr(exc)[:300]
 

@@ -50,7 +50,11 @@ def main():
     print("|---|" + "---|" * len(COLS))
     for n, p in sorted(zip(names, pretty), key=lambda t: t[1]):
         short = re.sub(r"^void ppnn::", "", p)
-        short = re.sub(r"\(.*$", "", short)
+        # keep the template arguments, drop the parameter list: cut at the "(" that follows the closing ">" (or the name)
+        m2 = re.match(r"^([A-Za-z0-9_:]+(?:<.*?>)?)\(ppnn::|^([A-Za-z0-9_:]+(?:<.*?>)?)\(", short)
+        if m2:
+            short = m2.group(1) or m2.group(2)
+        short = short.replace("(int)", "").replace("(bool)", "")
         print(f"| `{short}` | " + " | ".join(str(counts[n][c]) for c in COLS) + " |")
 
 

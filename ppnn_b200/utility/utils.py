@@ -22,6 +22,16 @@ def model_count(model):
     return sum(p.numel() for p in model.parameters())
 
 
+def numpy2string(x, format='(%.6g %.6g %.0g)'):
+    """Rows of ``x`` as text in an OpenFOAM vector-list format (utils.py:34-37; host-side helper of the OpenFOAM
+    bridge, kept so that ``from utility.utils import numpy2string`` resolves through the drop-in)."""
+    import io
+    import numpy as np
+    buf = io.StringIO()
+    np.savetxt(buf, x, fmt=format)
+    return buf.getvalue()
+
+
 def _hw(size: Size) -> Tuple[int, int]:
     if isinstance(size, (tuple, list)):
         if len(size) == 1:

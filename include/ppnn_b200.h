@@ -123,6 +123,13 @@ typedef struct ppnn_coarse_cfg {
 int ppnn_pde_du_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                     float* pdeu, int B, void* stream);
 
+/* The "iter" variant of pde_du in post_process/test2D2.py:70-91: `inner` sequential explicit sub-steps of the
+ * restricted coarse state (u1 <- u1 + dt*rhsu(u1,v1); v1 <- v1 + dt*rhsv(new u1, v1) on the halos of the old v1)
+ * before the increment dt*rhs is evaluated and prolonged; inner = 0 is ppnn_pde_du_fwd.  Forward only (the
+ * script uses it for inference).                                                              */
+int ppnn_pde_du_iter_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                         float* pdeu, int B, int inner, void* stream);
+
 /* Vector-Jacobian product of pde_du: grad_u [B,2,FH,FW] (overwritten) and
  * grad_mu [B] (overwritten; may be NULL).  add_identity != 0 returns
  * grad_out + J^T grad_out, the adjoint of  u -> u + pde_du(u).                  */

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "ppnn_resample_fwd_strided": (C.c_int, [_P, _P, C.c_long, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_resample_bwd": (C.c_int, [_P, _P, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_pde_du_fwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_int, _P]),
+    "ppnn_pde_du_iter_fwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.c_int, C.c_int, _P]),
     "ppnn_pde_du_bwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "ppnn_step_update_bwd": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, C.POINTER(C.c_float), _P, _P, _P, C.c_int, _P]),
     "ppnn_pde_du_fwd_save": (C.c_int, [C.POINTER(CoarseCfg), _P, _P, _P, _P, C.c_int, _P]),

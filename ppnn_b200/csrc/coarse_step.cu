@@ -65,6 +65,24 @@ coarse_step_kernel(const CoarseParams p, const StepIO io, const StepPlan pl) {
     }
     __syncthreads();
 
+    // ---- phase 1': the "iter" variant of pde_du (post_process/test2D2.py:72-79): `inner` sequential Euler sub-steps
+    // of the coarse state first -- u1 <- u1 + dt*rhsu(u1, v1), then v1 <- v1 + dt*rhsv(NEW u1, v1) on the halos of the
+    // OLD v1, exactly as the script writes it
+    for (int it = 0; it < io.inner; ++it) {
+        for (int idx = tid; idx < nn2; idx += kStepThreads) {
+            const int I = idx / p.NW, J = idx - I * p.NW;
+            ru[idx] = cu[idx] + p.dt * eval_rhs(p, p.rhs_u, cu, cu, cv, I, J, mu);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nn2; idx += kStepThreads) {
+            const int I = idx / p.NW, J = idx - I * p.NW;
+            rv[idx] = cv[idx] + p.dt * eval_rhs(p, p.rhs_v, cv, ru, cv, I, J, mu);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 2 * nn2; idx += kStepThreads) cu[idx] = ru[idx];     // cv follows cu, rv follows ru
+        __syncthreads();
+    }
+
     // ---- phase 2: dt * rhs on the periodic coarse grid ----------------------
     coarse_rhs_phase(p, cu, cv, ru, rv, mu, tid, kStepThreads);
     __syncthreads();
@@ -310,7 +328,8 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
     if (pl.band_rows < 1) { pl.band_rows = p.FH; pl.nband = 1; }
     // TMA-staged path: operands through a shared-memory ring (see coarse_step_staged.cuh)
     const bool nn_ok = !io.nn || (reinterpret_cast<uintptr_t>(io.nn) & 15) == 0;
-    if (pl.nchunk <= PPNN_STEP_WARPS && B < (1 << 30) && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok && !PPNN_ENV_OFF("PPNN_NO_TMA")) {
+    if (io.inner == 0 && pl.nchunk <= PPNN_STEP_WARPS && B < (1 << 30) && (p.FW - 1) % 4 == 0 && p.CH <= p.FH && nn_ok &&
+        !PPNN_ENV_OFF("PPNN_NO_TMA")) {
         StagedLayout lay;
         lay.ustage = MODE == MODE_PDEU ? 0 : (kStageRows * p.FW + 8 + 3) & ~3;
         lay.nstage = (MODE == MODE_UPDATE && io.nn) ? kStageRows * (p.FW - 1) : 0;
@@ -372,6 +391,15 @@ extern "C" int ppnn_pde_du_fwd_save(const ppnn_coarse_cfg* cfg, const float* u, 
 extern "C" int ppnn_pde_du_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
                                float* pdeu, int B, void* stream) {
     return ppnn_pde_du_fwd_save(cfg, u, mu, pdeu, nullptr, B, stream);
+}
+
+extern "C" int ppnn_pde_du_iter_fwd(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,
+                                    float* pdeu, int B, int inner, void* stream) {
+    if (!u || !mu || !pdeu) return PPNN_E_NULL;
+    if (inner < 0) return PPNN_E_SHAPE;
+    StepIO io = {};
+    io.u = u; io.mu = mu; io.out = pdeu; io.inner = inner;
+    return launch_step<MODE_PDEU>(cfg, io, B, stream);
 }
 
 extern "C" int ppnn_step_inputs(const ppnn_coarse_cfg* cfg, const float* u, const float* mu,

@@ -15,6 +15,7 @@ struct StepIO {
     float* u_norm;         // [B,2,FH-1,FW-1]                  (MODE_INPUTS)
     float* p_norm;         // [B,2,FH-1,FW-1] or null          (MODE_INPUTS)
     float* coarse;         // [B,2,CH-1,CW-1] or null: the restricted coarse state, saved for the adjoint pass
+    int inner;             // coarse Euler sub-steps before the increment is evaluated (post_process/test2D2.py:70-91)
     float m0[2], s0[2];    // inmean/instd   (INPUTS) | outmean/outstd (UPDATE)
     float m1[2], s1[2];    // pdemean/pdestd (INPUTS)
 };

@@ -180,6 +180,19 @@ class CoarseStep:
 
     __call__ = pde_du
 
+    @torch.no_grad()
+    def pde_du_iter(self, u: torch.Tensor, mu, inner: int = 1) -> torch.Tensor:
+        """The ``pde_du`` of post_process/test2D2.py:70-91: ``inner`` sequential explicit sub-steps of the restricted
+        coarse state (v sees the updated u) before the increment is evaluated and prolonged.  Inference only."""
+        self._check_state(u)
+        u = L.dev(u, "u")
+        muv = _mu_vec(mu, u.shape[0], u.device)
+        out = torch.empty_like(u)
+        with L.on_device(u):
+            L.check(L.load().ppnn_pde_du_iter_fwd(C.byref(self.cfg), u.data_ptr(), muv.data_ptr(), out.data_ptr(),
+                                                  u.shape[0], int(inner), L.stream()), "ppnn_pde_du_iter_fwd")
+        return out
+
     def step_inputs(self, u, mu, inmean, instd, pdemean=None, pdestd=None, want_pdeu=False):
         """Normalised network inputs of train2D.py:235-237 (no autograd):
         ``(u_norm, pdeu_norm | None, pdeu | None)``.  Statistics may be tensors

@@ -185,6 +185,24 @@ def make_pde_du(fine, cmesh, rhsu_name, rhsv_name, dt, length):
         return torch.cat((mcvter.up(padBC_rd(dt * rhsu(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, ux, uy, dx, dy, dx2, dy2))),
                           mcvter.up(padBC_rd(dt * rhsv(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, vx, vy, dx, dy, dx2, dy2)))),
                          dim=1)
+    def pde_du_iter(u, mu, inner=1):
+        """post_process/test2D2.py:70-91 (the script has range(1))."""
+        u1 = mcvter.down(u[:, :1])[:, :, :-1, :-1]
+        v1 = mcvter.down(u[:, 1:])[:, :, :-1, :-1]
+        for _ in range(inner):
+            ux = padbcx(u1)
+            uy = padbcy(u1)
+            vx = padbcx(v1)
+            vy = padbcy(v1)
+            u1 = u1+dt*rhsu(u1,v1,mu,dudx,dudy,d2udx2,d2udy2,ux,uy,dx,dy,dx2,dy2)
+            v1 = v1+dt*rhsv(u1,v1,mu,dudx,dudy,d2udx2,d2udy2,vx,vy,dx,dy,dx2,dy2)
+        ux = padbcx(u1)
+        uy = padbcy(u1)
+        vx = padbcx(v1)
+        vy = padbcy(v1)
+        return torch.cat((mcvter.up(padBC_rd(dt*rhsu(u1,v1,mu,dudx,dudy,d2udx2,d2udy2,ux,uy,dx,dy,dx2,dy2))),
+                          mcvter.up(padBC_rd(dt*rhsv(u1,v1,mu,dudx,dudy,d2udx2,d2udy2,vx,vy,dx,dy,dx2,dy2)))), dim=1)
+    pde_du.iter = pde_du_iter
     return pde_du, padBC_rd
 
 
@@ -207,6 +225,7 @@ def gen_pde_du():
         f, _ = make_pde_du(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
         mu = torch.tensor([c["mu"][1]]).reshape(1, 1, 1, 1)
         out[f"{name}/257"] = f(u257, mu)
+        out[f"{name}/257_iter1"] = f.iter(u257, mu, 1)
     save("pde_du_257.npz", **out)
 
     out = {}
@@ -232,6 +251,8 @@ def gen_pde_du():
         mm = mu.clone().requires_grad_(True)
         y = f(uu, mm)
         out[f"{name}/pdeu"] = y
+        out[f"{name}/pdeu_iter1"] = f.iter(u65, mu, 1)        # post_process/test2D2.py:70-91
+        out[f"{name}/pdeu_iter2"] = f.iter(u65, mu, 2)
         gu, gm = torch.autograd.grad(y, (uu, mm), cot)
         out[f"{name}/grad_u"] = gu
         out[f"{name}/grad_mu"] = gm

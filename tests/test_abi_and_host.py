@@ -61,6 +61,8 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert l.ppnn_fine_burgers_step(1, 2, 3, 1, 5, 1, 33, 33, 1, 0, 3, 6, 1e-4, .01, .01, None) == -6   # alias
     assert l.ppnn_fine_burgers_step(1, 2, 3, 4, 5, 1, 33, 33, 1, 9, 3, 6, 1e-4, .01, .01, None) == -6   # mode
     assert l.ppnn_pde_du_fwd(ctypes.byref(cfg), 1, 1, 1, 0, None) == 0                     # empty batch
+    assert l.ppnn_pde_du_iter_fwd(ctypes.byref(cfg), 1, 1, 1, 1, -1, None) == -2           # negative sub-step count
+    assert l.ppnn_pde_du_iter_fwd(ctypes.byref(cfg), 1, None, 1, 1, 1, None) == -1
     # small on-chip solvers
     assert l.ppnn_ks1d_rk4(None, None, 1, 1, 129, 1, 1, 3, 6, 4, 1e-4, .4, .16, .0256, None) == -1      # NULL
     assert l.ppnn_ks1d_rk4(1, None, 1, 1, 129, 1, 1, 3, 5, 4, 1e-4, .4, .16, .0256, None) == -3         # accuracy

@@ -272,6 +272,9 @@ def test_pde_du_full_size_against_reference_golden(pk, case):
     mu = torch.tensor([c["mu"]]).reshape(1, 1, 1, 1).cuda()
     ours = step.pde_du(g["u257"].cuda(), mu)
     assert_parity(ours.cpu(), g[f"{case}/257"], TOL, case)
+    # the "iter" variant of post_process/test2D2.py:70-91 (one coarse sub-step before the increment)
+    assert_parity(step.pde_du_iter(g["u257"].cuda(), mu, 1).cpu(), g[f"{case}/257_iter1"], TOL, case + " iter1")
+    assert_parity(step.pde_du_iter(g["u257"].cuda(), mu, 0).cpu(), g[f"{case}/257"], TOL, case + " iter0 = pde_du")
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
@@ -284,6 +287,8 @@ def test_pde_du_small_grads_update_rollout_against_reference_golden(pk, case):
     m = mu.clone().requires_grad_(True)
     y = step.pde_du(u, m)
     assert_parity(y.detach().cpu(), g[f"{case}/pdeu"], TOL, case + " pdeu")
+    for inner in (1, 2):
+        assert_parity(step.pde_du_iter(g["u65"].cuda(), mu, inner).cpu(), g[f"{case}/pdeu_iter{inner}"], TOL, f"{case} iter{inner}")
     gu, gm = torch.autograd.grad(y, (u, m), g["cot65"].cuda())
     assert_parity(gu.cpu(), g[f"{case}/grad_u"], TOL, case + " grad_u")
     if g[f"{case}/grad_mu"].abs().max() > 0:

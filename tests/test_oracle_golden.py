@@ -95,6 +95,7 @@ def test_pde_du_full_size(case):
     step = O.CoarseStep(257, c["cmesh"], c["rhsu"], c["rhsv"], c["dt"], c["length"])
     mu = torch.tensor([c["mu"]]).reshape(1, 1, 1, 1)
     assert_parity(step.pde_du(g["u257"], mu), g[f"{case}/257"], TOL, case)
+    assert_parity(step.pde_du_iter(g["u257"], mu, 1), g[f"{case}/257_iter1"], TOL, case + " iter variant (test2D2.py:70-91)")
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
@@ -107,6 +108,8 @@ def test_pde_du_small_with_grads_update_rollout(case):
     m = mu.clone().requires_grad_(True)
     y = step.pde_du(u, m)
     assert_parity(y.detach(), g[f"{case}/pdeu"], TOL, case + " pdeu")
+    for inner in (1, 2):
+        assert_parity(step.pde_du_iter(g["u65"], mu, inner), g[f"{case}/pdeu_iter{inner}"], TOL, f"{case} iter{inner}")
     gu, gm = torch.autograd.grad(y, (u, m), g["cot65"], allow_unused=True)
     assert_parity(gu, g[f"{case}/grad_u"], TOL, case + " grad_u")
     if gm is not None and g[f"{case}/grad_mu"].abs().max() > 0:

@@ -289,6 +289,13 @@ int ppnn_ks2d_rhs(const float* u, float* f_out, int B, int H, int W, int endpoin
 int ppnn_heat1d_pad(const float* u, const int* cls, const float* bv, float* out,
                     int B, int n, float dx, void* stream);
 
+/* Rollout update of the Bv workload (Bv/train.py:162, Bv/test.py:153):
+ *   out = padder(u[...,1:-1] + nn + pdeu[...,1:-1], cls, bv)
+ * u, pdeu, out [B, n+2] (padded states; pdeu may be NULL: the network-only model), nn [B, n].  out must not
+ * alias u or pdeu.                                                                             */
+int ppnn_heat1d_update(const float* u, const float* nn, const float* pdeu, const int* cls, const float* bv,
+                       float* out, int B, int n, float dx, void* stream);
+
 /* The generator loop of Bv/data.py:92-97, `nsteps` steps in one launch:
  *   up = padder(u, cls, bv);  u <- u + diffusion1D(accuracy=2)(up)/dx2*dt
  * padded_out (may be NULL) receives up = padder(u_in) BEFORE the first step (what the loop saves

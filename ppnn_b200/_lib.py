@@ -71,6 +71,7 @@ _SIGNATURES = {
     "ppnn_ks2d_rhs": (C.c_int, [_P] * 2 + [C.c_int] * 7 + [C.c_float] * 8 + [_P]),
     "ppnn_ks2d_rk4": (C.c_int, [_P] * 2 + [C.c_int] * 8 + [C.c_float] * 9 + [_P]),
     "ppnn_heat1d_pad": (C.c_int, [_P] * 4 + [C.c_int] * 2 + [C.c_float, _P]),
+    "ppnn_heat1d_update": (C.c_int, [_P] * 6 + [C.c_int] * 2 + [C.c_float, _P]),
     "ppnn_heat1d_bc_steps": (C.c_int, [_P] * 5 + [C.c_long] + [C.c_int] * 3 + [C.c_float] * 3 + [_P]),
     "ppnn_heat1d_coarse_increment": (C.c_int, [_P] * 4 + [C.c_int] * 3 + [C.c_float] * 3 + [_P]),
 }

@@ -486,6 +486,30 @@ heat1d_pad_kernel(const float* __restrict__ u, const int* __restrict__ cls, cons
     }
 }
 
+// rollout update of the Bv workload (Bv/train.py:162, Bv/test.py:153): padder(u[1:-1] + nn + pdeu[1:-1], cls, bv)
+__global__ void __launch_bounds__(256)
+heat1d_update_kernel(const float* __restrict__ u, const float* __restrict__ nn, const float* __restrict__ pdeu,
+                     const int* __restrict__ cls, const float* __restrict__ bv, float* __restrict__ out,
+                     long total, int n, float dx) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / (n + 2);
+        const int i = (int)(idx - b * (n + 2));
+        const float* ur = u + b * (n + 2);
+        const float* pr = pdeu ? pdeu + b * (n + 2) : nullptr;
+        const float* nr = nn + b * n;
+        auto inner = [&](int k) -> float {                        // interior point k of the new state
+            float v = ur[k + 1] + nr[k];
+            if (pr) v += pr[k + 1];
+            return v;
+        };
+        float v;
+        if (i == 0) v = bc_ghost(cls[2 * b], bv[2 * b], inner(0), dx);
+        else if (i == n + 1) v = bc_ghost(cls[2 * b + 1], bv[2 * b + 1], inner(n - 1), dx);
+        else v = inner(i - 1);
+        out[idx] = v;
+    }
+}
+
 }  // namespace ppnn
 
 using namespace ppnn;
@@ -579,6 +603,19 @@ extern "C" int ppnn_heat1d_pad(const float* u, const int* cls, const float* bv, 
     long blocks = (total + 255) / 256;
     if (blocks > 148L * 16) blocks = 148L * 16;
     heat1d_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(u, cls, bv, out, total, n, dx);
+    return launch_status();
+}
+
+extern "C" int ppnn_heat1d_update(const float* u, const float* nn, const float* pdeu, const int* cls, const float* bv,
+                                  float* out, int B, int n, float dx, void* stream) {
+    if (!u || !nn || !cls || !bv || !out) return PPNN_E_NULL;
+    if (B < 0 || n < 1) return PPNN_E_SHAPE;
+    if (out == u || out == pdeu) return PPNN_E_MODE;
+    if (B == 0) return PPNN_OK;
+    const long total = (long)B * (n + 2);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    heat1d_update_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(u, nn, pdeu, cls, bv, out, total, n, dx);
     return launch_status();
 }
 

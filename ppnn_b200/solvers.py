@@ -219,6 +219,28 @@ class HeatBC1D:
         return out
 
     @torch.no_grad()
+    def step_update(self, u: torch.Tensor, nn_out: torch.Tensor, pdeu: Optional[torch.Tensor],
+                    cls: torch.Tensor, bv: torch.Tensor) -> torch.Tensor:
+        """The rollout update of ``Bv/train.py:162`` / ``Bv/test.py``:
+        ``fpad(u[...,1:-1] + nnu + pdeu[...,1:-1], cls, bv)`` on the padded state ``u [B,1,n+2]``, the network
+        increment ``nn_out [B,1,n]`` and the coarse PDE increment ``pdeu [B,1,n+2]`` (None: network-only model)."""
+        u, shape = _as_batch(u, 1)
+        B, n = u.shape[0], u.shape[-1] - 2
+        nn_out = L.dev(nn_out, "nn_out")
+        if nn_out.numel() != B * n:
+            raise RuntimeError(f"nn_out has shape {tuple(nn_out.shape)}, expected [B,1,{n}]")
+        if pdeu is not None:
+            pdeu = L.dev(pdeu, "pdeu")
+            if pdeu.shape != u.shape:
+                raise RuntimeError(f"pdeu has shape {tuple(pdeu.shape)}, expected {tuple(u.shape)}")
+        c, b = self._bc(cls, bv, B, u.device)
+        out = torch.empty_like(u)
+        with L.on_device(u):
+            L.check(L.load().ppnn_heat1d_update(u.data_ptr(), nn_out.data_ptr(), L.ptr(pdeu), c.data_ptr(), b.data_ptr(),
+                                                out.data_ptr(), B, n, self.dx, L.stream()), "ppnn_heat1d_update")
+        return out.reshape(shape)
+
+    @torch.no_grad()
     def run(self, u: torch.Tensor, cls: torch.Tensor, bv: torch.Tensor, nsteps: int,
             padded_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``nsteps`` steps ``u <- u + diffusion1D(padder(u))/dx2*dt`` in ONE launch.  ``padded_out`` (a

@@ -74,6 +74,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert l.ppnn_ks1d_rhs(1, None, 1, 1, 129, 1, 3, 6, 4, .4, .16, .0256, None) == -6                   # f_out aliases u
     assert l.ppnn_ks2d_rhs(1, 2, 1, 129, 129, 1, 3, 6, 4, .1, 1., .4, .4, .16, .16, .0256, .0256, None) == -5
     assert l.ppnn_heat1d_pad(1, None, 1, 1, 2, 126, .4, None) == -1
+    assert l.ppnn_heat1d_update(1, 2, 3, 4, 5, 1, 2, 126, .4, None) == -6                                # out aliases u
     assert l.ppnn_heat1d_bc_steps(1, 1, 1, None, None, 0, 2, 126, 5, .01, .4, .16, None) == -1          # no output at all
     assert l.ppnn_heat1d_bc_steps(1, 1, 1, 1, 1, 100, 2, 126, 5, .01, .4, .16, None) == -2              # snapshot stride < n+2
     assert l.ppnn_heat1d_coarse_increment(1, 1, 1, 1, 2, 128, 32, .5, 1.6, 2.56, None) == -6            # out aliases u

@@ -213,6 +213,21 @@ def test_bv_heat_against_reference_golden(S):
         assert_parity(fwd(r, cls, bvr).cpu(), g["bv/pdeu"][:, t], TOL, f"genforward composed t={t}")
 
 
+def test_bv_rollout_update(S):
+    """Bv/train.py:162: u <- fpad(u[...,1:-1] + nnu + pdeu[...,1:-1], cls, bv), with and without the PDE increment"""
+    g = load_golden("solvers.npz")
+    cls, bvr, dx = g["bv/cls"], g["bv/BVr"], g["bv/dx"]
+    u = g["bv/results"][:, 1]
+    pdeu = g["bv/pdeu"][:, 1]
+    torch.manual_seed(5)
+    nn = 0.05 * torch.randn(u.shape[0], 1, u.shape[-1] - 2)
+    heat = S.HeatBC1D(float(g["bv/dt"]), float(dx))
+    ref = O.bv_pad(u[..., 1:-1] + nn + pdeu[..., 1:-1], cls, bvr, dx)
+    assert_parity(heat.step_update(u.cuda(), nn.cuda(), pdeu.cuda(), cls.cuda(), bvr.cuda()).cpu(), ref, TOL, "bv update")
+    ref0 = O.bv_pad(u[..., 1:-1] + nn, cls, bvr, dx)
+    assert_parity(heat.step_update(u.cuda(), nn.cuda(), None, cls.cuda(), bvr.cuda()).cpu(), ref0, TOL, "bv update, no pde")
+
+
 @pytest.mark.parametrize("n,b", [(126, 256), (30, 3), (5000, 4), (1, 2)])
 def test_bv_heat_sizes_against_oracle(S, n, b):
     torch.manual_seed(n + b)

@@ -14,7 +14,10 @@
 // one launch with one __syncthreads per stage (two for the 2-D case, whose mixed fourth derivative needs the
 // second-derivative fields of the stage first).  HBM is touched once on entry and once on exit, so the bound is
 // shared-memory issue rate, not bandwidth; there is nothing to stream and nothing for tensor cores.
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ppnn {
 
@@ -332,7 +335,7 @@ static int launch_ks2d_pts(const Ks2dParams& p, int B, size_t smem, void* stream
 }
 
 template <int HALO>
-static int launch_ks2d(Ks2dParams& p, int B, void* stream) {
+static int launch_ks2d_single(Ks2dParams& p, int B, void* stream) {
     const int N = p.H * p.W;
     p.FH = p.H + 2 * HALO; p.FW = p.W + 2 * HALO;
     p.invFW = 1.f / (float)p.FW;
@@ -345,6 +348,198 @@ static int launch_ks2d(Ks2dParams& p, int B, void* stream) {
     if (fits(8)) return launch_ks2d_pts<HALO, 8>(p, B, smem, stream);
     if (fits(16)) return launch_ks2d_pts<HALO, 16>(p, B, smem, stream);
     return launch_ks2d_pts<HALO, 24>(p, B, smem, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 2-D KS for FEW samples: one sample per THREAD-BLOCK CLUSTER (the reference runs a single 65^2 sample,
+// operators.py:754-757, which would leave 147 of 148 SMs idle).  The CS CTAs of a cluster own row slabs of the frame;
+// each keeps its slab + HALO ghost rows above and below in its own shared memory.  The thread that produces a stage
+// value stores it into every frame that shows it: its own, the ghost rows of the slab above / below (distributed
+// shared memory, st.shared::cluster through map_shared_rank) and -- for the rows next to the period's ends -- the
+// ghost rows of the first / last CTA, which hold the periodic images.  One cluster barrier per stage orders those
+// remote stores against the next stage's reads; with ping-pong stage buffers nothing else is needed.
+// ------------------------------------------------------------------------------------------------------------
+struct Ks2dSlab { int r0, n; };                       // first owned row, owned rows
+
+__host__ __device__ inline Ks2dSlab ks2d_slab(int H, int CS, int r) {
+    const int base = H / CS, rem = H % CS;
+    Ks2dSlab s;
+    s.r0 = r * base + (r < rem ? r : rem);
+    s.n = base + (r < rem ? 1 : 0);
+    return s;
+}
+
+template <int HALO, int CS, int PTS>
+__global__ void __launch_bounds__(512)
+ks2d_rk4_cluster_kernel(const Ks2dParams p) {
+    extern __shared__ float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / CS;
+    const Ks2dSlab me = ks2d_slab(p.H, CS, rank);
+    const int LFHmax = (p.H + CS - 1) / CS + 2 * HALO;          // same frame pitch in every CTA (remote offsets)
+    const int NFl = LFHmax * p.FW;
+    float* cur = sm;
+    float* nxt = sm + NFl;
+    float* LX = sm + 2 * NFl;
+    float* LY = sm + 3 * NFl;
+    const int T = blockDim.x;
+    const int N = p.H * p.W;
+    const float* uin = p.u + (size_t)b * N;
+    const int LFH = me.n + 2 * HALO;                            // this CTA's frame rows
+
+    // ---- frame of the initial state: every cell straight from global memory, periodic images by index ----
+    for (int cell = threadIdx.x; cell < LFH * p.FW; cell += T) {
+        const int fi = __float2int_rd(((float)cell + 0.5f) * p.invFW), fj = cell - fi * p.FW;
+        const int gi = wrap_axis(me.r0 - HALO + fi, p.H, p.PH), gj = wrap_axis(fj - HALO, p.W, p.PW);
+        cur[cell] = uin[gi * p.W + gj];
+    }
+
+    // ---- this thread's points and where their values have to go ----
+    float U[PTS], A[PTS];
+    int cellq[PTS], djq[PTS];                                   // local cell; column offset of the periodic image (0: none)
+    int adjq[PTS], imgq[PTS];                                   // (rank << 20 | local cell) of the copy in the adjacent slab's
+                                                                // ghost rows / in the ghost rows that hold the periodic image; -1: none
+    const int npts = me.n * p.W;
+#pragma unroll
+    for (int q = 0; q < PTS; ++q) {
+        const int idx = threadIdx.x + q * T;
+        U[q] = 0.f; A[q] = 0.f; cellq[q] = 0; djq[q] = 0; adjq[q] = -1; imgq[q] = -1;
+        if (idx < npts) {
+            const int li = __float2int_rd(((float)idx + 0.5f) * p.invW), j = idx - li * p.W;
+            const int gi = me.r0 + li;
+            cellq[q] = (li + HALO) * p.FW + j + HALO;
+            U[q] = uin[gi * p.W + j];
+            if (j >= p.PW - HALO && j < p.PW) djq[q] = -p.PW;
+            else if (j >= p.W - p.PW && j < p.W - p.PW + HALO) djq[q] = p.PW;
+            // ghost rows of the neighbouring slabs (slabs hold >= 2*HALO rows: a row is near one edge at most)
+            if (li < HALO && rank > 0) {
+                const Ks2dSlab up = ks2d_slab(p.H, CS, rank - 1);
+                adjq[q] = ((rank - 1) << 20) | ((up.n + HALO + li) * p.FW + j + HALO);
+            } else if (li >= me.n - HALO && rank < CS - 1) {
+                adjq[q] = ((rank + 1) << 20) | ((li - me.n + HALO) * p.FW + j + HALO);
+            }
+            // periodic images of the rows: gi - PH in [-HALO, -1] -> ghost rows above slab 0; gi + PH in [H, H+HALO) ->
+            // ghost rows below the last slab
+            if (gi >= p.PH - HALO && gi < p.PH) {
+                imgq[q] = (0 << 20) | ((gi - p.PH + HALO) * p.FW + j + HALO);
+            } else if (gi >= p.H - p.PH && gi < p.H - p.PH + HALO) {
+                const Ks2dSlab last = ks2d_slab(p.H, CS, CS - 1);
+                imgq[q] = ((CS - 1) << 20) | ((gi + p.PH - last.r0 + HALO) * p.FW + j + HALO);
+            }
+        }
+    }
+    auto store_all = [&](float* buf, int q, float v) {
+        buf[cellq[q]] = v;
+        if (djq[q]) buf[cellq[q] + djq[q]] = v;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int tg = t ? imgq[q] : adjq[q];
+            if (tg >= 0) {
+                float* rb = cluster.map_shared_rank(buf, tg >> 20);
+                const int c = tg & 0xfffff;
+                rb[c] = v;
+                if (djq[q]) rb[c + djq[q]] = v;
+            }
+        }
+    };
+    cluster.sync();                                             // every frame initialised before anyone stores into it
+
+    auto phase_a = [&]() {
+        for (int cell = threadIdx.x; cell < LFH * p.FW; cell += T) {
+            const int fi = __float2int_rd(((float)cell + 0.5f) * p.invFW), fj = cell - fi * p.FW;
+            if (fi >= HALO && fi < me.n + HALO) {               // LX on the owned rows, all frame columns
+                float ax = 0.f;
+#pragma unroll
+                for (int d = -HALO; d <= HALO; ++d) ax = fmaf(p.d2.c[d + HALO], cur[cell + d * p.FW], ax);
+                LX[cell] = ax;
+            }
+            if (fj >= HALO && fj < p.W + HALO) {                // LY on all frame rows, real columns
+                float ay = 0.f;
+#pragma unroll
+                for (int d = -HALO; d <= HALO; ++d) ay = fmaf(p.d2.c[d + HALO], cur[cell + d], ay);
+                LY[cell] = ay;
+            }
+        }
+    };
+
+    if (p.rhs_only) {
+        phase_a();
+        __syncthreads();
+        float* o = p.out + (size_t)b * N;
+#pragma unroll
+        for (int q = 0; q < PTS; ++q) {
+            const int idx = threadIdx.x + q * T;
+            if (idx < npts) o[me.r0 * p.W + idx] = ks2d_rhs<HALO>(p, cur, LX, LY, cellq[q]);
+        }
+        return;
+    }
+    for (int step = 0; step < p.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            phase_a();
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PTS; ++q) {
+                const int idx = threadIdx.x + q * T;
+                if (idx < npts) {
+                    const float k = ks2d_rhs<HALO>(p, cur, LX, LY, cellq[q]);
+                    store_all(nxt, q, rk4_advance(stage, k, U[q], A[q], p.dt));
+                }
+            }
+            cluster.sync();                                     // remote ghost rows of `nxt` complete, `cur` free for reuse
+            float* t = cur; cur = nxt; nxt = t;
+        }
+    }
+    float* o = p.out + (size_t)b * N;
+#pragma unroll
+    for (int q = 0; q < PTS; ++q) {
+        const int idx = threadIdx.x + q * T;
+        if (idx < npts) o[me.r0 * p.W + idx] = U[q];
+    }
+}
+
+template <int HALO, int CS>
+static int launch_ks2d_cluster(Ks2dParams& p, int B, void* stream, bool* used) {
+    *used = false;
+    if (p.H / CS < 2 * HALO) return PPNN_OK;                    // slabs too thin for the one-edge rule
+    p.FH = p.H + 2 * HALO; p.FW = p.W + 2 * HALO;
+    p.invFW = 1.f / (float)p.FW;
+    const int rows = (p.H + CS - 1) / CS;
+    const int npts = rows * p.W;
+    if (npts > 2 * 512 || (rows + 2 * HALO) * p.FW >= (1 << 20)) return PPNN_OK;
+    const size_t smem = (size_t)4 * (rows + 2 * HALO) * p.FW * sizeof(float);
+    if (smem > 200 * 1024) return PPNN_OK;
+    const bool two = npts > 512;
+    const int per = two ? (npts + 1) / 2 : npts;
+    const int T = ((per + 31) / 32) * 32;
+    void (*kern)(Ks2dParams) = two ? ks2d_rk4_cluster_kernel<HALO, CS, 2> : ks2d_rk4_cluster_kernel<HALO, CS, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CS), 1, 1);
+    cfg.blockDim = dim3((unsigned)T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return (int)e;
+    *used = true;
+    return launch_status();
+}
+
+// few samples: spread each over a cluster of 8 (<= 18 samples) or 4 (<= 37) SMs; otherwise one CTA per sample
+template <int HALO>
+static int launch_ks2d(Ks2dParams& p, int B, void* stream) {
+    bool used = false;
+    int st = PPNN_OK;
+    if (B * 8 <= 148) st = launch_ks2d_cluster<HALO, 8>(p, B, stream, &used);
+    if (st == PPNN_OK && !used && B * 4 <= 148) st = launch_ks2d_cluster<HALO, 4>(p, B, stream, &used);
+    if (used || st != PPNN_OK) return st;
+    return launch_ks2d_single<HALO>(p, B, stream);
 }
 
 // common host side: stencil tables of a KS solver on ONE halo

@@ -36,6 +36,18 @@ def test_ks2d_against_reference_golden(S):
     for i in range(3):                                   # one launch per step
         u = ks.rk4(u)
         assert_parity(u.cpu(), g[f"ks2d/u{i + 1}"], TOL, f"ks2d step {i + 1}")
+    # <= 37 samples run one sample per thread-block cluster (row slabs + DSMEM ghost rows), more run one per CTA:
+    # the same golden vectors through the other kernel (scaled copies behind them so that the samples differ), and
+    # the two kernels against each other bit for bit
+    scale = torch.cat((torch.ones(1), torch.linspace(0.5, 1.5, 19))).reshape(-1, 1, 1, 1, 1)
+    many = (g["ks2d/u0"].unsqueeze(0) * scale).reshape(40, 1, 65, 65).cuda()
+    fm, um = ks.f(many), ks.rk4(many)
+    assert_parity(fm[:2].cpu(), g["ks2d/f0"], TOL, "ks2d f, one CTA per sample")
+    assert_parity(um[:2].cpu(), g["ks2d/u1"], TOL, "ks2d step, one CTA per sample")
+    few_f = torch.cat([ks.f(many[k:k + 2]) for k in range(0, 40, 2)])
+    few_u = torch.cat([ks.run(many[k:k + 2], 2) for k in range(0, 40, 2)])
+    assert torch.equal(fm, few_f), "f: cluster kernel and single-CTA kernel differ"
+    assert torch.equal(ks.run(many, 2), few_u), "2 steps: cluster kernel and single-CTA kernel differ"
     u3 = ks.run(g["ks2d/u0"].cuda(), 3)                  # three steps inside one launch
     assert torch.equal(u3, u), "multi-step launch differs from step-by-step launches"
     assert_parity(u3.cpu(), g["ks2d/u3"], TOL, "ks2d 3 steps in one launch")

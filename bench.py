@@ -662,6 +662,12 @@ def run_ours(args):
         t = timed(lambda: fb.step_(a, b_, mf, a2, b2), reps * 2, 3)
         extras["fine_burgers_step_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
                                                "hbm_gbs": 8 * fpts / t / 1e6}
+        # the same on all-positive fields like the generator's own (initial conditions in [0.1, 1.1], operators.py:436-445)
+        ap, bp = a + 0.6, b_ + 0.6
+        t = timed(lambda: fb.step_(ap, bp, mf, a2, b2), reps * 2, 3)
+        extras["fine_burgers_step_1025x64_positive_fields"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,
+                                                               "hbm_gbs": 8 * fpts / t / 1e6}
+        del ap, bp
         fbi = FineBurgers(mode="intended")
         t = timed(lambda: fbi.step_(a, b_, mf, a2, b2), reps * 2, 3)
         extras["fine_burgers_step_intended_1025x64"] = {"ms": t, "gpts": world * fpts / t / 1e6, "bytes_per_pt": 8,

@@ -22,6 +22,12 @@
 
 namespace ppnn {
 
+#ifdef PPNN_TRACE
+// dev-only timeline of the CTAs (entry, end of the prologue, end of the stream, SM id); never in the shipped library
+__device__ unsigned long long g_trace[6 * 8192];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 struct DatasetIO {
     const float* u;          // sample b = planes [slot(b)*2, slot(b)*2+2) of this array
     const float* x;          // the state one step later, same slots
@@ -37,21 +43,31 @@ struct DatasetIO {
 };
 
 // PER > 0: compile-time prolongation period for the reference's meshes (see coarse_step_staged.cuh)
-template <int FWC, bool EMIT, int PER = 0, int ADV = 0>
+#ifndef PPNN_NST_DS49
+#define PPNN_NST_DS49 4
+#endif
+#ifndef PPNN_NST_DS33
+#define PPNN_NST_DS33 4
+#endif
+// ring depths (see coarse_step.cu): 5 / 6 stages of 16.5 KB fit but do not pay (statistics 0.402 vs 0.407 ms)
+constexpr int kNstDs49 = PPNN_NST_DS49, kNstDs33 = PPNN_NST_DS33;
+
+template <int FWC, bool EMIT, int PER = 0, int ADV = 0, int NST = kStages>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl, const StagedLayout lay, const PhaseWeights pw) {
     extern __shared__ float4 smem4[];
+    const int trows = PER > 0 ? 0 : p.FH, tints = PER > 0 ? 0 : (p.FH + 2 * lay.nsteps + 3) & ~3;
     float4* roww = smem4;
-    int* rowi = reinterpret_cast<int*>(roww + p.FH);
-    int* rowadv = rowi + p.FH;
+    int* rowi = reinterpret_cast<int*>(roww + trows);
+    int* rowadv = rowi + trows;
     const int nn2 = p.NH * p.NW;
-    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 2 * lay.nsteps + 3) & ~3));
+    float* cu = reinterpret_cast<float*>(rowi + tints);
     float* cv = cu + nn2;
     float* rf = cv + nn2;
-    float* sU = cu + ((3 * nn2 + 3) & ~3);                      // [kStages][2][ustage]
-    float* sX = sU + (size_t)kStages * 2 * lay.ustage;          // [kStages][2][ustage]
-    __shared__ __align__(8) uint64_t full[kStages];
-    __shared__ __align__(8) uint64_t empty[kStages];
+    float* sU = cu + ((3 * nn2 + 3) & ~3);                      // [NST][2][ustage]
+    float* sX = sU + (size_t)NST * 2 * lay.ustage;          // [NST][2][ustage]
+    __shared__ __align__(8) uint64_t full[NST];
+    __shared__ __align__(8) uint64_t empty[NST];
     __shared__ double red[PPNN_STEP_WARPS][6];
 
     const int FW = FWC ? FWC : p.FW;
@@ -86,7 +102,7 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         return nb;
     };
     auto issue = [&](int t) {
-        const int s = t % kStages;
+        const int s = t % NST;
         // expected bytes first (same arithmetic as band()), then the copies
         uint32_t total = 0;
 #pragma unroll
@@ -118,12 +134,15 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
     };
 
     const bool producer = warp == PPNN_STEP_WARPS;
+#ifdef PPNN_TRACE
+    if (tid == 0 && blockIdx.x < 8192) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); g_trace[6 * blockIdx.x] = gtime(); g_trace[6 * blockIdx.x + 3] = sm; }
+#endif
     if (producer) {
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
+            for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
             fence_barrier_init();
-            for (int t = 0; t < kStages && t < lay.nsteps; ++t) issue(t);
+            for (int t = 0; t < NST && t < lay.nsteps; ++t) issue(t);
         }
     } else {
         // ---- phase 1: restriction gather + row tables (as coarse_step_staged_kernel) ----
@@ -133,6 +152,9 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         if (PER == 0) build_row_tables(p, lay.split, lay.nsteps, kStageRows, roww, rowi, rowadv, tid, kStepThreads);
     }
     __syncthreads();
+#ifdef PPNN_TRACE
+    if (tid == 0 && blockIdx.x < 8192) g_trace[6 * blockIdx.x + 4] = gtime();
+#endif
 
     // ---- phase 2: dt * rhs of this CTA's field ----
     if (!producer) {
@@ -149,11 +171,14 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         }
     }
     __syncthreads();
+#ifdef PPNN_TRACE
+    if (tid == 0 && blockIdx.x < 8192) g_trace[6 * blockIdx.x + 1] = gtime();
+#endif
 
     if (producer) {
         if (lane == 0) {
-            for (int t = kStages; t < lay.nsteps; ++t) {
-                mbar_wait(&empty[t % kStages], ((t / kStages) - 1) & 1);
+            for (int t = NST; t < lay.nsteps; ++t) {
+                mbar_wait(&empty[t % NST], ((t / NST) - 1) & 1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(t);
             }
@@ -227,6 +252,7 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
             const float* sx = sx_base;
             int s = 0; uint32_t ph = 0;
             int base = g ? SPLIT * ADV / PER : 0;
+            float2 A_u = make_float2(0.f, 0.f), A_uu = A_u, A_p = A_u, A_pp = A_u, A_l = A_u, A_ll = A_u;
             float h[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) h[k] = yrow(base - 1 + k);
@@ -252,7 +278,7 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
             auto advance = [&]() {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
-                if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
+                if (++s == NST) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
                 else { su += ustep; sx += ustep; }
                 if (EMIT) { unp += (size_t)R * PW; pnp += (size_t)R * PW; lnp += (size_t)R * PW; }
             };
@@ -260,11 +286,36 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
 #pragma unroll
                 for (int bnd = 0; bnd < PER / R; ++bnd) {
                     mbar_wait_addr(full_a + 8u * s, ph);
-#pragma unroll
-                    for (int q = 0; q < R; ++q) {
+                    auto pde_row = [&](int q) -> float {
                         const int r = bnd * R + q;
                         const int o = (r * ADV) / PER;
-                        emit(q, h[o] * pw.w[r][0] + h[o + 1] * pw.w[r][1] + h[o + 2] * pw.w[r][2] + h[o + 3] * pw.w[r][3], false);
+                        return h[o] * pw.w[r][0] + h[o + 1] * pw.w[r][1] + h[o + 2] * pw.w[r][2] + h[o + 3] * pw.w[r][3];
+                    };
+#ifdef PPNN_DBG_NOCOMPUTE
+                    if (false) {
+                    } else if (true) {
+                        A_p.x += su[0];
+#else
+                    if constexpr (EMIT) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) emit(q, pde_row(q), false);
+#endif
+                    } else {
+                        // statistics: two rows per packed fp32x2 instruction (8 issue slots per row pair
+                        // instead of 16 for the two differences and six accumulations)
+#pragma unroll
+                        for (int q = 0; q < R; q += 2) {
+                            const float2 pde = make_float2(pde_row(q), pde_row(q + 1));
+                            const float2 uu = make_float2(su[q * FW], su[(q + 1) * FW]);
+                            const float2 xx = make_float2(sx[q * FW], sx[(q + 1) * FW]);
+                            const float2 m1 = make_float2(-1.f, -1.f);
+                            // (u_{t+1} - u_t) - pdeu in the reference's order: a * -1 + b rounds once, like b - a
+                            const float2 lab = __ffma2_rn(pde, m1, __ffma2_rn(uu, m1, xx));
+                            A_p = __fadd2_rn(A_p, pde);  A_pp = __ffma2_rn(pde, pde, A_pp);
+                            if (DUPL && dupl) { A_p = __fadd2_rn(A_p, pde);  A_pp = __ffma2_rn(pde, pde, A_pp); }
+                            A_u = __fadd2_rn(A_u, uu);   A_uu = __ffma2_rn(uu, uu, A_uu);
+                            A_l = __fadd2_rn(A_l, lab);  A_ll = __ffma2_rn(lab, lab, A_ll);
+                        }
                     }
                     advance();
                 }
@@ -275,6 +326,10 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
             if (g == 1) {                                       // row 256: on the last coarse node, outside the cropped arrays
                 mbar_wait_addr(full_a + 8u * s, ph);
                 emit(0, h[1], true);
+            }
+            if (!EMIT) {
+                a_u += A_u.x + A_u.y; a_uu += A_uu.x + A_uu.y; a_p += A_p.x + A_p.y;
+                a_pp += A_pp.x + A_pp.y; a_l += A_l.x + A_l.y; a_ll += A_ll.x + A_ll.y;
             }
         };
         if ((warp & 7) == 0) stream_rows(std::true_type{}); else stream_rows(std::false_type{});
@@ -347,7 +402,7 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         auto advance = [&]() {
             __syncwarp();
             if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
-            if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
+            if (++s == NST) { s = 0; ph ^= 1u; su = su_base; sx = sx_base; }
             else { su += ustep; sx += ustep; }
             wrow += kStageRows;
             if (EMIT) { unp += (size_t)kStageRows * PW; pnp += (size_t)kStageRows * PW; lnp += (size_t)kStageRows * PW; }
@@ -369,6 +424,9 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
         }
     }
 
+#ifdef PPNN_TRACE
+    if (tid == 0 && blockIdx.x < 8192) g_trace[6 * blockIdx.x + 2] = gtime();
+#endif
     if (!EMIT) {
         // deterministic reduction: lanes -> warp (shuffles, fp64), warps -> CTA in warp order
         double v[6] = {(double)a_u, (double)a_uu, (double)a_p, (double)a_pp, (double)a_l, (double)a_ll};
@@ -409,10 +467,6 @@ static int run_dataset(const ppnn_coarse_cfg* cfg, DatasetIO io, long B, bool em
     int n0 = (lay.split + kStageRows - 1) / kStageRows;
     int n1 = (p.FH - lay.split + kStageRows - 1) / kStageRows;
     lay.nsteps = n0 > n1 ? n0 : n1;
-    size_t smem = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + 3) & ~3) * sizeof(int) +
-                  (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
-                  (size_t)kStages * 2 * 2 * lay.ustage * sizeof(float);
-    if (smem > 200 * 1024) return PPNN_E_TOOBIG;
     const size_t plane2 = (size_t)2 * p.FH * p.FW;
     const size_t last = (size_t)(io.T > 0 ? (B - 1) + (B - 1) / io.T : B - 1);
     io.u_end = io.u + (last + 1) * plane2;
@@ -420,21 +474,37 @@ static int run_dataset(const ppnn_coarse_cfg* cfg, DatasetIO io, long B, bool em
     void (*kern)(CoarseParams, DatasetIO, StepPlan, StagedLayout, PhaseWeights);
     const bool square = p.FH == 257 && p.FW == 257 && p.CH == p.CW && lay.split == 128 && pl.nchunk == 8 &&
                         !PPNN_ENV_OFF("PPNN_NO_PERIODIC");
-    int per = 0;
-    if (square && p.CH == 49)      { per = 16; kern = emit ? dataset_pass_kernel<257, true, 16, 3> : dataset_pass_kernel<257, false, 16, 3>; }
-    else if (square && p.CH == 33) { per = 8;  kern = emit ? dataset_pass_kernel<257, true, 8, 1> : dataset_pass_kernel<257, false, 8, 1>; }
+    // compile-time period: no run-time tables, ring as deep as two resident CTAs allow (stages of 16.5 KB)
+    int per = 0, nst = kStages;
+    if (square && p.CH == 49)      { per = 16; nst = kNstDs49; kern = emit ? dataset_pass_kernel<257, true, 16, 3, kNstDs49> : dataset_pass_kernel<257, false, 16, 3, kNstDs49>; }
+    else if (square && p.CH == 33) { per = 8;  nst = kNstDs33; kern = emit ? dataset_pass_kernel<257, true, 8, 1, kNstDs33> : dataset_pass_kernel<257, false, 8, 1, kNstDs33>; }
     else if (p.FW == 257) kern = emit ? dataset_pass_kernel<257, true> : dataset_pass_kernel<257, false>;
     else                  kern = emit ? dataset_pass_kernel<0, true> : dataset_pass_kernel<0, false>;
+    const size_t tables = per ? 0 : (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + 3) & ~3) * sizeof(int);
+    const size_t smem = tables + (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
+                        (size_t)nst * 2 * 2 * lay.ustage * sizeof(float);
+    if (smem > 200 * 1024) return PPNN_E_TOOBIG;
+#ifdef PPNN_DBG_SMEM
+    const size_t smem_launch = PPNN_DBG_SMEM;
+#else
+    const size_t smem_launch = smem;
+#endif
     const PhaseWeights pw = make_phase_weights(p.suh, per);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)(2 * B), kStagedThreads, smem, (cudaStream_t)stream>>>(p, io, pl, lay, pw);
+    kern<<<(unsigned)(2 * B), kStagedThreads, smem_launch, (cudaStream_t)stream>>>(p, io, pl, lay, pw);
     return launch_status();
 }
 
 }  // namespace ppnn
 
 using namespace ppnn;
+
+#ifdef PPNN_TRACE
+extern "C" int ppnn_trace_read(unsigned long long* host, long n) {
+    return (int)cudaMemcpyFromSymbol(host, g_trace, (size_t)n * sizeof(unsigned long long));
+}
+#endif
 
 extern "C" int ppnn_dataset_stats(const ppnn_coarse_cfg* cfg, const float* u, const float* u_next, const float* mu,
                                   long B, long traj_len, double* partial, void* stream) {

@@ -306,6 +306,22 @@ static int launch_step_fw(const CoarseParams& p, const StepIO& io, const StepPla
     return launch_status();
 }
 
+// Ring depths of the compile-time-period instantiations (they carry no run-time tables, which leaves room for more
+// stages next to the 27 / 12 KB of coarse state at two CTAs per SM).  Same-box timings, 1920 samples: stages of
+// 16.5 KB (u + network operand) gain nothing beyond 4 (0.4716 / 0.4715 ms with 4 / 5); the single-operand modes
+// (8.3 KB per stage) want 8: PDE-only update 0.357 -> 0.334 ms (10 stages: 0.354, the elected lane issues them
+// serially at entry).
+#ifndef PPNN_NST_NN49
+#define PPNN_NST_NN49 4
+#endif
+#ifndef PPNN_NST_NN33
+#define PPNN_NST_NN33 4
+#endif
+#ifndef PPNN_NST_U
+#define PPNN_NST_U 8
+#endif
+constexpr int kNstNN49 = PPNN_NST_NN49, kNstNN33 = PPNN_NST_NN33, kNstU = PPNN_NST_U;
+
 template <int MODE>
 static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void* stream) {
     CoarseParams p;
@@ -342,29 +358,30 @@ static int launch_step(const ppnn_coarse_cfg* cfg, const StepIO& io, int B, void
             int n1 = (p.FH - lay.split + kStageRows - 1) / kStageRows;
             lay.nsteps = n0 > n1 ? n0 : n1;
         }
-        size_t smem2 = (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + 3) & ~3) * sizeof(int) +
-                       (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
-                       (size_t)kStages * 2 * (lay.ustage + lay.nstage) * sizeof(float);
+        const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
+        const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
+        void (*kern)(CoarseParams, StepIO, StepPlan, StagedLayout, const float*, PhaseWeights);
+        // the reference's own meshes: prolongation period unrolled at compile time (16 fine rows per 3 coarse
+        // rows for 257 -> 49, 8 per 1 for 257 -> 33), no run-time tables, and the ring as deep as two resident
+        // CTAs allow (kNst*: stages of 16.5 KB with the network operand, 8.3 KB without)
+        const bool square = p.FH == 257 && p.FW == 257 && p.CH == p.CW && lay.split == 128 && pl.nchunk == 8 &&
+                            !PPNN_ENV_OFF("PPNN_NO_PERIODIC");
+        int per = 0, nst = kStages;
+        if (square && p.CH == 49) {
+            per = 16; nst = has_nn ? kNstNN49 : kNstU;
+            kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 16, 3, kNstNN49> : coarse_step_staged_kernel<MODE, 257, false, 16, 3, kNstU>;
+        } else if (square && p.CH == 33) {
+            per = 8; nst = has_nn ? kNstNN33 : kNstU;
+            kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 8, 1, kNstNN33> : coarse_step_staged_kernel<MODE, 257, false, 8, 1, kNstU>;
+        } else if (p.FW == 257) {
+            kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true> : coarse_step_staged_kernel<MODE, 257, false>;
+        } else {
+            kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
+        }
+        const size_t tables = per ? 0 : (size_t)p.FH * sizeof(float4) + (size_t)((p.FH + 2 * lay.nsteps + 3) & ~3) * sizeof(int);
+        const size_t smem2 = tables + (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
+                             (size_t)nst * 2 * (lay.ustage + lay.nstage) * sizeof(float);
         if (smem2 <= 200 * 1024) {
-            const float* u_end = io.u + (size_t)B * 2 * p.FH * p.FW;
-            const bool has_nn = MODE == MODE_UPDATE && io.nn != nullptr;
-            void (*kern)(CoarseParams, StepIO, StepPlan, StagedLayout, const float*, PhaseWeights);
-            // the reference's own meshes: prolongation period unrolled at compile time (16 fine rows per 3 coarse
-            // rows for 257 -> 49, 8 per 1 for 257 -> 33)
-            const bool square = p.FH == 257 && p.FW == 257 && p.CH == p.CW && lay.split == 128 && pl.nchunk == 8 &&
-                                !PPNN_ENV_OFF("PPNN_NO_PERIODIC");
-            int per = 0;
-            if (square && p.CH == 49) {
-                per = 16;
-                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 16, 3> : coarse_step_staged_kernel<MODE, 257, false, 16, 3>;
-            } else if (square && p.CH == 33) {
-                per = 8;
-                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true, 8, 1> : coarse_step_staged_kernel<MODE, 257, false, 8, 1>;
-            } else if (p.FW == 257) {
-                kern = has_nn ? coarse_step_staged_kernel<MODE, 257, true> : coarse_step_staged_kernel<MODE, 257, false>;
-            } else {
-                kern = has_nn ? coarse_step_staged_kernel<MODE, 0, true> : coarse_step_staged_kernel<MODE, 0, false>;
-            }
             const PhaseWeights pw = make_phase_weights(p.suh, per);
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return (int)e;

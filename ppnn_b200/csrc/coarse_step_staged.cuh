@@ -148,6 +148,7 @@ struct StagedLayout {
 
 
 constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 producer warp
+
 // One CTA = one (sample, field) plane.  Consumer warp = (row group g, 32-column
 // chunk): group 0 walks rows [0, split), group 1 rows [split, FH), both fed by
 // the same ring step.  HAS_NN: the update adds the network output (MODE_UPDATE).
@@ -157,7 +158,8 @@ constexpr int kStagedThreads = kStepThreads + 32;   // 16 consumer warps + 1 pro
 // by exactly ADV rows and the PER weight phases repeat.  The consumer loop is then unrolled over one period:
 // which window entries a row uses, and when new ones are computed, is decided at compile time, and the
 // weights (`pw`, a kernel parameter) are constant-bank operands.  PER == 0: any mesh, run-time tables.
-template <int MODE, int FWC, bool HAS_NN, int PER = 0, int ADV = 0>
+// NST: ring depth (chosen per instantiation in the launchers from same-box timings).
+template <int MODE, int FWC, bool HAS_NN, int PER = 0, int ADV = 0, int NST = kStages>
 __global__ void __launch_bounds__(kStagedThreads, PPNN_MINCTA)
 coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan pl, const StagedLayout lay,
                           const float* u_end, const PhaseWeights pw) {
@@ -166,17 +168,19 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     // cap (12 bytes of spills in the band loop, 0.485 -> 0.494 ms) while the issue-bound modes gain 2-10 %.
     constexpr bool FASTDIV = !(MODE == MODE_UPDATE && HAS_NN);
     extern __shared__ float4 smem4[];
+    // run-time prolongation tables (PER == 0 only; the compile-time period needs none)
+    const int trows = PER > 0 ? 0 : p.FH, tints = PER > 0 ? 0 : (p.FH + 2 * lay.nsteps + 3) & ~3;
     float4* roww = smem4;                                       // [FH] H-pass weights
-    int* rowi = reinterpret_cast<int*>(roww + p.FH);            // [FH] floor(i * suh)
-    int* rowadv = rowi + p.FH;                                  // [2][nsteps] bit q: row rs_g + R*t + q moves the window
+    int* rowi = reinterpret_cast<int*>(roww + trows);           // [FH] floor(i * suh)
+    int* rowadv = rowi + trows;                                 // [2][nsteps] bit q: row rs_g + R*t + q moves the window
     const int nn2 = p.NH * p.NW;
-    float* cu = reinterpret_cast<float*>(rowi + ((p.FH + 2 * lay.nsteps + 3) & ~3));
+    float* cu = reinterpret_cast<float*>(rowi + tints);
     float* cv = cu + nn2;
     float* rf = cv + nn2;                                       // dt * rhs of this CTA's field
-    float* sU = cu + ((3 * nn2 + 3) & ~3);                      // [kStages][2][ustage], 16-byte aligned
-    float* sN = sU + (size_t)kStages * 2 * lay.ustage;          // [kStages][2][nstage]
-    __shared__ __align__(8) uint64_t full[kStages];
-    __shared__ __align__(8) uint64_t empty[kStages];
+    float* sU = cu + ((3 * nn2 + 3) & ~3);                      // [NST][2][ustage], 16-byte aligned
+    float* sN = sU + (size_t)NST * 2 * lay.ustage;          // [NST][2][nstage]
+    __shared__ __align__(8) uint64_t full[NST];
+    __shared__ __align__(8) uint64_t empty[NST];
 
     const int FW = FWC ? FWC : p.FW;
     const int PW = FW - 1, PH = p.FH - 1;
@@ -194,9 +198,9 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     const int rid = f ? p.rhs_v : p.rhs_u;
 
     const uint64_t pol_stream = l2_policy_evict_first();
-    // producer: bulk copies of ring step t (kStageRows rows of each row group) into slot t % kStages
+    // producer: bulk copies of ring step t (kStageRows rows of each row group) into slot t % NST
     auto issue = [&](int t) {
-        const int s = t % kStages;
+        const int s = t % NST;
         uintptr_t a0[2]; uint32_t nb[2] = {0, 0}, nnb[2] = {0, 0}; int nr0[2] = {0, 0};
         uint32_t total = 0;
         const uintptr_t end_al = reinterpret_cast<uintptr_t>(u_end) & ~(uintptr_t)15;
@@ -231,9 +235,9 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     if (producer) {
         if (lane == 0 && MODE != MODE_PDEU) {
 #pragma unroll
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
+            for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nconsumers); }
             fence_barrier_init();
-            for (int t = 0; t < kStages && t < lay.nsteps; ++t) issue(t);   // in flight during phases 1 and 2
+            for (int t = 0; t < NST && t < lay.nsteps; ++t) issue(t);   // in flight during phases 1 and 2
         }
     } else {
         // ---- phase 1: restriction gather (loads of kGatherBatch points in flight) + row tables ----
@@ -269,8 +273,8 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
     if (producer) {
         // ---- producer warp: refill a slot as soon as every consumer warp released it ----
         if (lane == 0 && MODE != MODE_PDEU) {
-            for (int t = kStages; t < lay.nsteps; ++t) {
-                mbar_wait(&empty[t % kStages], ((t / kStages) - 1) & 1);
+            for (int t = NST; t < lay.nsteps; ++t) {
+                mbar_wait(&empty[t % NST], ((t / NST) - 1) & 1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(t);
             }
@@ -382,7 +386,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
                 if (MODE != MODE_PDEU) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);
-                    if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
+                    if (++s == NST) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
                     else { su += ustep; sn += nstep; }
                 }
                 if (op) op += (size_t)R * FW;
@@ -489,7 +493,7 @@ coarse_step_staged_kernel(const CoarseParams p, const StepIO io, const StepPlan 
         if (MODE != MODE_PDEU) {
             __syncwarp();
             if (lane == 0) mbar_arrive_addr(empty_a + 8u * s);  // this warp is done with slot s
-            if (++s == kStages) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
+            if (++s == NST) { s = 0; ph ^= 1u; su = su_base; sn = sn_base; }
             else { su += ustep; sn += nstep; }
         }
         wrow += kStageRows;

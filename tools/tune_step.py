@@ -32,6 +32,19 @@ st = [L.f2([0.0, 0.0]), L.f2([0.3, 0.3]), L.f2([0.0, 0.0]), L.f2([1e-3, 1e-3])]
 res["inputs"] = t(lambda: step.step_inputs(u, mu, *st))
 res["burgers_update"] = t(lambda: bstep.step_update_(u, mu * 0.05, nn, om, os_, out))
 res["pde_du"] = t(lambda: step.pde_du(u, mu))
+import ctypes as C
+lib = L.load()
+x = u + 1e-3 * torch.randn_like(u)
+partial = torch.zeros(B, 2, 6, dtype=torch.float64, device=dev)
+outs = [torch.empty(B, 2, F - 1, F - 1, device=dev) for _ in range(3)]
+m6, s6 = (C.c_float * 6)(0.1, 0.2, 0.0, 0.0, 0.0, 0.0), (C.c_float * 6)(0.3, 0.3, 1e-3, 1e-3, 1e-3, 1e-3)
+for nm, st_ in (("rd", step), ("b33", bstep)):
+    muv = mu if nm == "rd" else mu * 0.05
+    res["stats_" + nm] = t(lambda: L.check(lib.ppnn_dataset_stats(C.byref(st_.cfg), u.data_ptr(), x.data_ptr(), muv.data_ptr(), B, 0,
+                                                                   partial.data_ptr(), L.stream()), "stats"))
+    res["emit_" + nm] = t(lambda: L.check(lib.ppnn_dataset_emit(C.byref(st_.cfg), u.data_ptr(), x.data_ptr(), muv.data_ptr(), B, 0, m6, s6,
+                                                                 outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), L.stream()), "emit"))
+res = {k: round(v, 4) if k != "checksum" else v for k, v in res.items()}
 print(json.dumps(res))
 ''' % ROOT
 for lib in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so"))):

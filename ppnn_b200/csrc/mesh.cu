@@ -141,6 +141,14 @@ resample_adjoint_kernel(const ResampleParams p, long total_in) {
 // per-row H weights come from a shared table built once per CTA.
 constexpr int kUpBand = 64;      // output rows per CTA
 
+// Write-only kernels on rows of 257 floats run at the store path's rate, not the HBM's: rows start on every 4-byte
+// phase, so a warp's 128-byte store touches five 32-byte sectors, two of them partially.  Ordinary (write-back)
+// stores: in the whole-plane kernel the streaming hint costs 20 % (0.207 vs 0.169 ms for 2160 planes 33^2 -> 257^2).
+// Tried and dropped (same box): rows staged in shared memory and written as 16-byte-aligned vectors (0.31 ms: one
+// barrier per 4 rows), the plane as a linear array of aligned float4 with the H pass from a W-interpolated copy
+// of the source in shared memory (0.27 ms: ~18 instructions per output).
+__device__ __forceinline__ void up_store(float* p, float v) { *p = v; }
+
 __global__ void __launch_bounds__(128)
 bicubic_up_kernel(const ResampleParams p) {
     __shared__ float4 roww[kUpBand];
@@ -181,7 +189,58 @@ bicubic_up_kernel(const ResampleParams p) {
             else { h0 = wpass(i0 - 1); h1 = wpass(i0); h2 = wpass(i0 + 1); h3 = wpass(i0 + 2); }
             base = i0;
         }
-        st_stream(out, h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w);
+        up_store(out, h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w);
+    }
+}
+
+// Whole-plane variant for small sources (every coarse mesh of the reference: 33^2, 49^2): CTA = one plane, the
+// source plane and the per-row tables live in shared memory, thread = output column walking ALL rows (the W pass
+// reads shared memory instead of gathering from global).  Same expressions as bicubic_up_kernel: bit-identical.
+__global__ void __launch_bounds__(1024)
+bicubic_up_plane_kernel(const ResampleParams p) {
+    extern __shared__ float4 up_smem[];
+    float4* roww = up_smem;                                              // [Hout]
+    int* rowi = reinterpret_cast<int*>(roww + p.Hout);                   // [Hout]
+    float* sin = reinterpret_cast<float*>(rowi + ((p.Hout + 3) & ~3));   // [Hin * Win]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const float* in = p.in + (size_t)blockIdx.x * p.in_stride;
+    for (int idx = tid; idx < p.Hin * p.Win; idx += nthr) sin[idx] = __ldg(in + idx);
+    for (int i = tid; i < p.Hout; i += nthr) {
+        const float si = resample_src(p.sh, i, p.align, true);
+        const float fi = floorf(si);
+        float w[4];
+        cubic_weights(si - fi, w);
+        rowi[i] = (int)fi;
+        roww[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+    for (int j = tid; j < p.Wout; j += nthr) {
+        const float sj = resample_src(p.sw, j, p.align, true);
+        const float fj = floorf(sj);
+        const int j0 = (int)fj;
+        float wj[4];
+        cubic_weights(sj - fj, wj);
+        const float* q0 = sin + clampi(j0 - 1, 0, p.Win - 1);
+        const float* q1 = sin + clampi(j0, 0, p.Win - 1);
+        const float* q2 = sin + clampi(j0 + 1, 0, p.Win - 1);
+        const float* q3 = sin + clampi(j0 + 2, 0, p.Win - 1);
+        auto wpass = [&](int I) -> float {
+            const int o = clampi(I, 0, p.Hin - 1) * p.Win;
+            return q0[o] * wj[0] + q1[o] * wj[1] + q2[o] * wj[2] + q3[o] * wj[3];
+        };
+        float* out = p.out + (size_t)blockIdx.x * p.Hout * p.Wout + j;
+        int base = rowi[0];
+        float h0 = wpass(base - 1), h1 = wpass(base), h2 = wpass(base + 1), h3 = wpass(base + 2);
+        for (int i = 0; i < p.Hout; ++i, out += p.Wout) {
+            const int i0 = rowi[i];
+            const float4 wx = roww[i];
+            if (i0 != base) {
+                if (i0 == base + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = wpass(i0 + 2); }
+                else { h0 = wpass(i0 - 1); h1 = wpass(i0); h2 = wpass(i0 + 1); h3 = wpass(i0 + 2); }
+                base = i0;
+            }
+            up_store(out, h0 * wx.x + h1 * wx.y + h2 * wx.z + h3 * wx.w);
+        }
     }
 }
 
@@ -209,6 +268,14 @@ static int run_resample(const float* in, float* out, long planes, long in_stride
     long blocks = (p.total + 255) / 256;
     if (blocks > 148L * 32) blocks = 148L * 32;
     unsigned g = (unsigned)blocks;
+    const size_t up_smem = (size_t)Hout * sizeof(float4) + (size_t)((Hout + 3) & ~3) * sizeof(int) + (size_t)Hin * Win * sizeof(float);
+    if (mode == PPNN_BICUBIC && !bwd && up_smem <= 96 * 1024 && planes < (1L << 31)) {
+        cudaError_t e = cudaFuncSetAttribute(bicubic_up_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
+        if (e != cudaSuccess) return (int)e;
+        const int threads = Wout >= 1024 ? 1024 : (Wout + 31) & ~31;
+        bicubic_up_plane_kernel<<<(unsigned)planes, threads, up_smem, s>>>(p);
+        return launch_status();
+    }
     if (mode == PPNN_BICUBIC && !bwd && planes <= 65535 && (Hout + kUpBand - 1) / kUpBand <= 65535) {
         dim3 grid((Wout + 127) / 128, (Hout + kUpBand - 1) / kUpBand, (unsigned)planes);
         bicubic_up_kernel<<<grid, 128, 0, s>>>(p);

@@ -216,8 +216,94 @@ rhs2d_tile_kernel(const RhsParams p, const float* ay_end) {
     }
 }
 
+// ---- whole-plane variant for small grids (every coarse mesh of the reference: 32^2, 48^2) ----
+// The tile kernel above is laid out for rows of >= 512 columns; on a 32-column grid a quarter of one warp
+// of each of its CTAs works.  Here CTA = one sample: its four operands (contiguous per sample) are staged in
+// shared memory by coalesced loads, thread = column j and row i0 of a sweep of 256 / W rows.  Same
+// arithmetic as the tile kernel (div_by, skipped zero taps of Upwind1).
+template <int K>
+__device__ __forceinline__ float rhs_point(const RhsParams& p, const float* xw, const float* yw, float u1, float v1, float mu) {
+    float acc = 0.f;
+    if (p.rhs_id & PPNN_RHS_ADV) {
+        float fx = 0.f, fy = 0.f;
+        if (p.adv_upwind) {
+            constexpr int C = (K - 1) / 2;
+            float bx = 0.f, by = 0.f;
+#pragma unroll
+            for (int k = C; k < K; ++k) { fx += p.aa[k] * xw[k]; fy += p.aa[k] * yw[k]; }
+#pragma unroll
+            for (int k = 0; k <= C; ++k) { bx += p.ab[k] * xw[k]; by += p.ab[k] * yw[k]; }
+            const float c1 = xw[C], c2 = yw[C];
+            fx = c1 <= 0.f ? fx : (c1 > 0.f ? bx : 0.f);
+            fy = c2 <= 0.f ? fy : (c2 > 0.f ? by : 0.f);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { fx += p.aa[k] * xw[k]; fy += p.aa[k] * yw[k]; }
+        }
+        acc = div_by(-u1 * fx, p.dx, p.rdx) - div_by(v1 * fy, p.dy, p.rdy);
+    }
+    if (p.rhs_id & PPNN_RHS_DIFF) {
+        float lx = 0.f, ly = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { lx += p.d[k] * xw[k]; ly += p.d[k] * yw[k]; }
+        const float lap = mu * (div_by(lx, p.dx2, p.rdx2) + div_by(ly, p.dy2, p.rdy2));
+        acc = (p.rhs_id & PPNN_RHS_ADV) ? acc + lap : lap;
+    }
+    return add_reaction(acc, p.rhs_id & ~3, u1, v1);
+}
+
+constexpr int kRPlaneThreads = 256;
+
+template <int K>
+__global__ void __launch_bounds__(kRPlaneThreads)
+rhs2d_plane_kernel(const RhsParams p) {
+    extern __shared__ __align__(16) float smem_rhs[];
+    const int Hx = p.H + 2 * p.halo, Wy = p.W + 2 * p.halo;
+    const int nx = Hx * p.W, ny = p.H * Wy, no = p.H * p.W;
+    float* sax = smem_rhs;
+    float* say = sax + ((nx + 3) & ~3);
+    float* su = say + ((ny + 3) & ~3);
+    float* sv = su + ((no + 3) & ~3);
+    const int t = threadIdx.x;
+    const long b = blockIdx.x;
+    auto stage = [&](float* dst, const float* src, int n) {
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && n % 4 == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int k = t; k < n / 4; k += kRPlaneThreads) d4[k] = __ldcs(s4 + k);
+        } else {
+            for (int k = t; k < n; k += kRPlaneThreads) dst[k] = ld_stream(src + k);
+        }
+    };
+    stage(sax, p.ax + (size_t)b * nx, nx);
+    stage(say, p.ay + (size_t)b * ny, ny);
+    stage(su, p.u1 + (size_t)b * no, no);
+    stage(sv, p.v1 + (size_t)b * no, no);
+    const float mu = __ldg(p.mu + b);
+    __syncthreads();
+    const int rps = kRPlaneThreads / p.W;                       // rows per sweep (W <= 128)
+    const int ib = t / p.W, j = t - ib * p.W;
+    if (ib >= rps) return;
+    float* out = p.out + (size_t)b * no;
+    for (int i = ib; i < p.H; i += rps) {
+        float xw[K], yw[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { xw[k] = sax[(i + k) * p.W + j]; yw[k] = say[i * Wy + j + k]; }
+        const int o = i * p.W + j;
+        st_stream(out + o, rhs_point<K>(p, xw, yw, su[o], sv[o], mu));
+    }
+}
+
 template <int K>
 static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
+    const size_t plane_smem = (size_t)((((p.H + 2 * p.halo) * p.W + 3) & ~3) + ((p.H * (p.W + 2 * p.halo) + 3) & ~3) +
+                                       2 * ((p.H * p.W + 3) & ~3)) * sizeof(float);
+    if (p.W <= 128 && plane_smem <= 100 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rhs2d_plane_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem);
+        if (e != cudaSuccess) return (int)e;
+        rhs2d_plane_kernel<K><<<(unsigned)B, kRPlaneThreads, plane_smem, s>>>(p);
+        return launch_status();
+    }
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (K > 1 && p.W % 4 == 0 && al(p.u1) && al(p.v1) && al(p.ax) && al(p.out) &&
         p.H <= 65535) {

@@ -1081,6 +1081,18 @@ def test_mesh_converter_on_channel_slices(pk):
     assert g1[:, 0].abs().max() == 0
 
 
+def test_bicubic_up_large_source_takes_the_band_kernel(pk):
+    """Sources that do not fit the whole-plane kernel's shared memory (> 96 KB: here 160 x 163) go through
+    bicubic_up_kernel; both must agree with ATen's upsample_bicubic2d (operators.py via utils.py:28-31)."""
+    gen = torch.Generator().manual_seed(21)
+    M = pk["mesh"]
+    for (hin, win, hout, wout) in ((160, 163, 301, 257), (21, 25, 301, 257)):
+        x = torch.randn(3, 1, hin, win, generator=gen).cuda()
+        m = M((hout, wout), (hin, win), dim=2)
+        ref = torch.nn.functional.interpolate(x, size=(hout, wout), mode="bicubic", align_corners=True)
+        assert_parity(m.up(x).cpu(), ref.cpu(), TOL, f"up {hin}x{win} -> {hout}x{wout}")
+
+
 def test_end_to_end_example_runs(pk):
     """examples/train_one_step.py: generator -> PdeDataset -> one-step training -> captured rollout, tiny sizes."""
     import importlib.util

@@ -387,6 +387,12 @@ extern "C" int ppnn_step_update_bwd(const ppnn_coarse_cfg* cfg, const float* u, 
     return run_adjoint(cfg, u, nullptr, mu, grad_out, grad_u, grad_mu, grad_nn, outstd, B, 1, stream);
 }
 
+#ifdef PPNN_TRACE
+extern "C" int ppnn_trace_read_adj(unsigned long long* host, long n) {
+    return (int)cudaMemcpyFromSymbol(host, ppnn::g_trace_adj, (size_t)n * sizeof(unsigned long long));
+}
+#endif
+
 extern "C" int ppnn_pde_du_bwd_saved(const ppnn_coarse_cfg* cfg, const float* coarse_state, const float* mu,
                                      const float* grad_out, float* grad_u, float* grad_mu,
                                      int B, int add_identity, void* stream) {

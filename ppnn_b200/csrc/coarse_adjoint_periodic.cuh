@@ -117,6 +117,15 @@ __device__ __forceinline__ float stencil_adjoint_t(const CoarseParams& p, int id
     return acc;
 }
 
+#ifdef PPNN_TRACE
+// dev-only CTA timeline (tools/trace_adjoint.py); never in the shipped library
+__device__ unsigned long long g_trace_adj[8 * 8192];
+__device__ __forceinline__ unsigned long long gtime_adj() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PPNN_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_trace_adj[8 * blockIdx.x + (k)] = gtime_adj(); } while (0)
+#else
+#define PPNN_STAMP(k) do { } while (0)
+#endif
+
 constexpr int kPerF = 257;                                  // fine points of the meshes this kernel takes
 constexpr int kPerApitch = 273;                             // A row pitch: odd, 16 zero columns after the 257
 constexpr int kPerApad = 16;                                // zero floats in front of A (left pad of row 0)
@@ -164,6 +173,10 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
     float* of = a.gu + ((size_t)b * 2 + f) * plane;              // ... and of grad_u
     const float mu = __ldg(a.mu + b);
     const bool producer = warp == kAdjWarps;
+    PPNN_STAMP(0);
+#ifdef PPNN_TRACE
+    if (tid == 0 && blockIdx.x < 8192) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); g_trace_adj[8 * blockIdx.x + 7] = sm; }
+#endif
 
     auto issue = [&](int t) {
         const int s = t % kAdjStages;
@@ -314,6 +327,7 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
         if ((warp & 7) == 0) stream_rows(std::true_type{}); else stream_rows(std::false_type{});
     }
     __syncthreads();              // A complete, ring dead, this CTA's base values of grad_u written
+    PPNN_STAMP(1);
 
     // ---- coarse state: bulk copy of the saved one (flies during phase 2) --------------------
     const int rid_own = f ? p.rhs_v : p.rhs_u, rid_oth = f ? p.rhs_u : p.rhs_v;
@@ -386,6 +400,7 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
     }
     if (a.coarse) mbar_wait(&cbar, 0);
     __syncthreads();
+    PPNN_STAMP(2);
 
     // ---- grad_mu partial of this field (needs only local data) ----
     const float* own = f ? cv : cu;
@@ -422,6 +437,7 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
         cluster.sync();                                           // both are done reading each other
     }
 
+    PPNN_STAMP(3);
     // ---- phase 3 + 4: own field's coarse cotangent, scatter through D_down^T ------
     for (int idx = tid; idx < NN2; idx += kAdjThreads) {
         const int I = small_div(idx, NC), J = idx - I * NC;
@@ -457,6 +473,7 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
             if (t.lj != 0.f) atomicAdd(o2 + t.dj, t.li * t.lj * cot);
         }
     }
+    PPNN_STAMP(4);
 }
 
 }  // namespace ppnn

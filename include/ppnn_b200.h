@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PPNN_B200_ABI_VERSION 3
+#define PPNN_B200_ABI_VERSION 4
 
 /* ---- status codes --------------------------------------------------------- */
 #define PPNN_OK            0
@@ -91,6 +91,18 @@ int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
                    int B, int H, int W, int halo, int rhs_id,
                    int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
                    float dx, float dy, float dx2, float dy2, void* stream);
+
+/* The same with u1 / v1 read in place from a strided view: rows of W floats every
+ * uv_row_pitch floats, samples every uv_plane_stride floats -- the view
+ * down(u)[:, :, :-1, :-1] of a [B,1,N+1,N+1] tensor that train2D.py:68-69 passes
+ * (no contiguous copy).  Grids of at most 128 columns (every coarse mesh of the
+ * reference); PPNN_E_SHAPE otherwise, and the caller copies.                     */
+int ppnn_rhs2d_fwd_strided(const float* u1, const float* v1, const float* mu,
+                           const float* ax, const float* ay, float* out,
+                           int B, int H, int W, int halo, int rhs_id,
+                           int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
+                           float dx, float dy, float dx2, float dy2,
+                           long uv_plane_stride, int uv_row_pitch, void* stream);
 
 /* mesh_convertor.down / .up (src/utility/utils.py:24,27-31): torch
  * F.interpolate(mode='bilinear'|'bicubic', size=(Hout,Wout), align_corners).    */

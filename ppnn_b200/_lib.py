@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPNN_B200_LIB") or os.path.join(_HERE, "libppnn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 E_NULL, E_SHAPE, E_TOOBIG = -1, -2, -5   # status codes of include/ppnn_b200.h used by the host code
 
 # enums of include/ppnn_b200.h
@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ppnn_stencil_fwd": (C.c_int, [_P, _P, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ppnn_stencil_bwd": (C.c_int, [_P, _P, _P, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ppnn_rhs2d_fwd": (C.c_int, [_P] * 6 + [C.c_int] * 9 + [C.c_float] * 4 + [_P]),
+    "ppnn_rhs2d_fwd_strided": (C.c_int, [_P] * 6 + [C.c_int] * 9 + [C.c_float] * 4 + [C.c_long, C.c_int, _P]),
     "ppnn_resample_fwd": (C.c_int, [_P, _P, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_resample_fwd_strided": (C.c_int, [_P, _P, C.c_long, C.c_long] + [C.c_int] * 6 + [_P]),
     "ppnn_resample_bwd": (C.c_int, [_P, _P, C.c_long] + [C.c_int] * 6 + [_P]),
@@ -127,9 +128,19 @@ class _NoCtx:
 _NOCTX = _NoCtx()
 
 
+# torch.cuda.current_device() / current_stream() are Python-level and cost ~1.5 / ~14 us per call -- more than
+# the launch they precede at rollout batch sizes (tools/profile_tier_host.py); the C bindings behind them do not.
+_cuda_get_device = getattr(torch._C, "_cuda_getDevice", None)
+_cuda_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _current_device() -> int:
+    return _cuda_get_device() if _cuda_get_device is not None else torch.cuda.current_device()
+
+
 def on_device(t: torch.Tensor):
     """Context that makes ``t``'s device current -- free when it already is."""
-    if t.device.index == torch.cuda.current_device():
+    if t.device.index == _current_device():
         return _NOCTX
     return torch.cuda.device(t.device)
 
@@ -139,6 +150,9 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def stream() -> int:
+    """Raw handle of the current stream of the current device (what every C entry point takes)."""
+    if _cuda_raw_stream is not None:
+        return _cuda_raw_stream(_current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -16,6 +16,8 @@ struct RhsParams {
     float dx, dy, dx2, dy2;
     float rdx, rdy, rdx2, rdy2;   // reciprocals for div_by (correctly rounded quotient without the division sequence)
     long total;
+    long uv_plane;                // floats between consecutive samples of u1 / v1 (H*W when dense)
+    int uv_pitch;                 // floats between consecutive rows of u1 / v1 (W when dense; plane kernel only)
 };
 
 constexpr int kRhsRows = 4;     // output rows per thread: the x-direction window is loaded once for all of them
@@ -277,8 +279,20 @@ rhs2d_plane_kernel(const RhsParams p) {
     };
     stage(sax, p.ax + (size_t)b * nx, nx);
     stage(say, p.ay + (size_t)b * ny, ny);
-    stage(su, p.u1 + (size_t)b * no, no);
-    stage(sv, p.v1 + (size_t)b * no, no);
+    if (p.uv_pitch == p.W) {
+        stage(su, p.u1 + (size_t)b * p.uv_plane, no);
+        stage(sv, p.v1 + (size_t)b * p.uv_plane, no);
+    } else {
+        // u1 / v1 as the reference passes them: the view down(u)[:, :, :-1, :-1] of a [B,1,N+1,N+1] tensor
+        // (train2D.py:68-69) -- read in place instead of through a contiguous copy
+        const float* gu = p.u1 + (size_t)b * p.uv_plane;
+        const float* gv = p.v1 + (size_t)b * p.uv_plane;
+        for (int k = t; k < no; k += kRPlaneThreads) {
+            const int i = k / p.W, j = k - i * p.W;
+            su[k] = ld_stream(gu + (size_t)i * p.uv_pitch + j);
+            sv[k] = ld_stream(gv + (size_t)i * p.uv_pitch + j);
+        }
+    }
     const float mu = __ldg(p.mu + b);
     __syncthreads();
     const int rps = kRPlaneThreads / p.W;                       // rows per sweep (W <= 128)
@@ -298,6 +312,8 @@ template <int K>
 static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
     const size_t plane_smem = (size_t)((((p.H + 2 * p.halo) * p.W + 3) & ~3) + ((p.H * (p.W + 2 * p.halo) + 3) & ~3) +
                                        2 * ((p.H * p.W + 3) & ~3)) * sizeof(float);
+    const bool dense = p.uv_pitch == p.W && p.uv_plane == (long)p.H * p.W;
+    if (!dense && !(p.W <= 128 && plane_smem <= 100 * 1024)) return PPNN_E_SHAPE;   // strided u1 / v1: whole-plane kernel only
     if (p.W <= 128 && plane_smem <= 100 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(rhs2d_plane_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem);
         if (e != cudaSuccess) return (int)e;
@@ -324,13 +340,13 @@ static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
 
 using namespace ppnn;
 
-extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
-                              const float* ax, const float* ay, float* out,
-                              int B, int H, int W, int halo, int rhs_id,
-                              int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
-                              float dx, float dy, float dx2, float dy2, void* stream) {
+static int run_rhs2d(const float* u1, const float* v1, const float* mu,
+                     const float* ax, const float* ay, float* out,
+                     int B, int H, int W, int halo, int rhs_id,
+                     int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
+                     float dx, float dy, float dx2, float dy2, long uv_plane, int uv_pitch, void* stream) {
     if (!u1 || !v1 || !mu || !ax || !ay || !out) return PPNN_E_NULL;
-    if (B < 0 || H < 1 || W < 1 || halo < 0) return PPNN_E_SHAPE;
+    if (B < 0 || H < 1 || W < 1 || halo < 0 || uv_pitch < W || uv_plane < (long)(H - 1) * uv_pitch + W) return PPNN_E_SHAPE;
     if (!valid_rhs_id(rhs_id)) return PPNN_E_RHS;
     RhsParams p;
     p.K = 2 * halo + 1;
@@ -353,13 +369,14 @@ extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
     p.dx = dx; p.dy = dy; p.dx2 = dx2; p.dy2 = dy2;
     p.rdx = 1.f / dx; p.rdy = 1.f / dy; p.rdx2 = 1.f / dx2; p.rdy2 = 1.f / dy2;
     p.total = (long)B * H * W;
+    p.uv_plane = uv_plane; p.uv_pitch = uv_pitch;
     if ((H + kRhsRows - 1) / kRhsRows > 65535) return PPNN_E_SHAPE;
     cudaStream_t s = (cudaStream_t)stream;
     // samples ride on gridDim.z (<= 65535): larger batches go out as several launches
     const size_t axs = (size_t)(H + 2 * halo) * W, ays = (size_t)H * (W + 2 * halo), os = (size_t)H * W;
     for (long b0 = 0; b0 < B; b0 += 65535) {
         const int n = (int)(B - b0 < 65535 ? B - b0 : 65535);
-        p.u1 = u1 + b0 * os; p.v1 = v1 + b0 * os; p.mu = mu + b0; p.ax = ax + b0 * axs; p.ay = ay + b0 * ays;
+        p.u1 = u1 + b0 * uv_plane; p.v1 = v1 + b0 * uv_plane; p.mu = mu + b0; p.ax = ax + b0 * axs; p.ay = ay + b0 * ays;
         p.out = out + b0 * os;
         p.total = (long)n * H * W;
         int st;
@@ -374,4 +391,23 @@ extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
         if (st != PPNN_OK) return st;
     }
     return PPNN_OK;
+}
+
+extern "C" int ppnn_rhs2d_fwd(const float* u1, const float* v1, const float* mu,
+                              const float* ax, const float* ay, float* out,
+                              int B, int H, int W, int halo, int rhs_id,
+                              int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
+                              float dx, float dy, float dx2, float dy2, void* stream) {
+    return run_rhs2d(u1, v1, mu, ax, ay, out, B, H, W, halo, rhs_id, adv_scheme, adv_accuracy, diff_scheme, diff_accuracy,
+                     dx, dy, dx2, dy2, (long)H * W, W, stream);
+}
+
+extern "C" int ppnn_rhs2d_fwd_strided(const float* u1, const float* v1, const float* mu,
+                                      const float* ax, const float* ay, float* out,
+                                      int B, int H, int W, int halo, int rhs_id,
+                                      int adv_scheme, int adv_accuracy, int diff_scheme, int diff_accuracy,
+                                      float dx, float dy, float dx2, float dy2,
+                                      long uv_plane_stride, int uv_row_pitch, void* stream) {
+    return run_rhs2d(u1, v1, mu, ax, ay, out, B, H, W, halo, rhs_id, adv_scheme, adv_accuracy, diff_scheme, diff_accuracy,
+                     dx, dy, dx2, dy2, uv_plane_stride, uv_row_pitch, stream);
 }

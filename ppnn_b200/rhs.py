@@ -135,13 +135,37 @@ def _mu_vector(mu, B, device):
     return torch.full((B,), float(mu), dtype=torch.float32, device=device)
 
 
+def _cropped_view(u1, v1, halo):
+    """(plane stride, row pitch) when u1 and v1 are the same kind of row-dense strided view of small planes --
+    ``down(u)[:, :, :-1, :-1]`` (train2D.py:68-69) -- that ``ppnn_rhs2d_fwd_strided`` reads in place; else None."""
+    if u1.is_contiguous() or u1.stride() != v1.stride():
+        return None
+    B, _, H, W = u1.shape
+    sb, _, sh, sw = u1.stride()
+    if sw != 1 or sh < W or sb < (H - 1) * sh + W or W > 128:
+        return None
+    if 4 * ((H + 2 * halo) * W + H * (W + 2 * halo) + 2 * H * W + 12) > 100 * 1024:     # the whole-plane kernel's shared memory
+        return None
+    return sb, sh
+
+
 def _fused_forward(u1, v1, mu, ax, ay, rid, halo, adv, dif, scal):
     lib = L.load()
     B, _, H, W = u1.shape
-    u1c, v1c, axc, ayc = (L.dev(t) for t in (u1, v1, ax, ay))
+    axc, ayc = L.dev(ax), L.dev(ay)
     muv = _mu_vector(mu, B, u1.device)
-    out = torch.empty_like(u1c)
     dx, dy, dx2, dy2 = scal
+    view = _cropped_view(u1, v1, halo)
+    if view is not None:
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=u1.device)
+        with L.on_device(u1):
+            L.check(lib.ppnn_rhs2d_fwd_strided(u1.data_ptr(), v1.data_ptr(), muv.data_ptr(), axc.data_ptr(),
+                                               ayc.data_ptr(), out.data_ptr(), B, H, W, halo, rid,
+                                               adv[0], adv[1], dif[0], dif[1], dx, dy, dx2, dy2,
+                                               view[0], view[1], L.stream()), "ppnn_rhs2d_fwd_strided")
+        return out, (u1, v1, muv, axc, ayc)
+    u1c, v1c = L.dev(u1), L.dev(v1)
+    out = torch.empty_like(u1c)
     with L.on_device(u1c):
         L.check(lib.ppnn_rhs2d_fwd(u1c.data_ptr(), v1c.data_ptr(), muv.data_ptr(), axc.data_ptr(),
                                    ayc.data_ptr(), out.data_ptr(), B, H, W, halo, rid,

@@ -188,6 +188,37 @@ def test_rhs_fused_gradients(pk):
             assert_parity(a.cpu(), b, 2e-5, f"{name} grad_{what}")
 
 
+def test_rhs_reads_cropped_views_in_place(pk):
+    """train2D.py:68-69 passes ``u1 = down(u)[:, :, :-1, :-1]`` -- a strided view -- to the rhs functions: the strided
+    entry point (ppnn_rhs2d_fwd_strided) must give exactly what the dense one gives on a contiguous copy."""
+    gen = torch.Generator().manual_seed(33)
+    ops, rhs = pk["ops"], pk["rhs"]
+    dudx, dudy, d2x, d2y = ops.dudx_2D(accuracy=1), ops.dudy_2D(accuracy=1), ops.d2udx2_2D(accuracy=2), ops.d2udy2_2D(accuracy=2)
+    for n in (32, 48, 7):
+        full_u = torch.randn(5, 1, n + 1, n + 1, generator=gen).cuda()
+        full_v = torch.randn(5, 1, n + 1, n + 1, generator=gen).cuda()
+        u1, v1 = full_u[:, :, :-1, :-1], full_v[:, :, :-1, :-1]
+        assert not u1.is_contiguous()
+        mu = torch.linspace(0.02, 0.07, 5).reshape(-1, 1, 1, 1).cuda()
+        for name in ("burgers2Dpu", "rdFv", "burgers2DFu"):
+            fld = v1 if name.endswith("v") else u1
+            ax, ay = O.wrap_x(fld, 1), O.wrap_y(fld, 1)
+            f = getattr(rhs, name)
+            a = f(u1, v1, mu, dudx, dudy, d2x, d2y, ax, ay, 0.1, 0.1, 0.01, 0.01)
+            b = f(u1.contiguous(), v1.contiguous(), mu, dudx, dudy, d2x, d2y, ax, ay, 0.1, 0.1, 0.01, 0.01)
+            assert a.is_contiguous() and torch.equal(a, b), f"{name} n={n}"
+    # gradients flow through the strided path as through the dense one
+    ur = full_u.clone().requires_grad_(True)
+    u1 = ur[:, :, :-1, :-1]
+    y = rhs.burgers2DFu(u1, v1, mu, dudx, dudy, d2x, d2y, O.wrap_x(u1, 1), O.wrap_y(u1, 1), 0.1, 0.1, 0.01, 0.01)
+    (g1,) = torch.autograd.grad(y.sum(), ur)
+    uc = full_u.clone().requires_grad_(True)
+    u1c = uc[:, :, :-1, :-1].contiguous()
+    y2 = rhs.burgers2DFu(u1c, v1.contiguous(), mu, dudx, dudy, d2x, d2y, O.wrap_x(u1c, 1), O.wrap_y(u1c, 1), 0.1, 0.1, 0.01, 0.01)
+    (g2,) = torch.autograd.grad(y2.sum(), uc)
+    assert_parity(g1.cpu(), g2.cpu(), TOL, "grad through the strided rhs")
+
+
 def test_mesh_converter_against_reference_golden(pk):
     g = load_golden("mesh.npz")
     M = pk["mesh"]

@@ -179,39 +179,54 @@ rhs2d_tile_kernel(const RhsParams p, const float* ay_end) {
         case 2: rtile_ywindow<K, 2>(srow, t, yw); break;
         default: rtile_ywindow<K, 3>(srow, t, yw); break;
         }
+        // two column pairs per thread, each on packed fp32x2 arithmetic (FFMA2: one issue slot, two columns; the
+        // kernel is issue-bound at ~120 scalar instructions per output).  Same operations in the same order per
+        // element as the scalar form (sums in tap order starting from fma(a, x, 0), div_by): bit-identical results.
         float res[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float u1 = uu[c], v1 = vv[c];
-            float acc = 0.f;
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * h;
+            const float2 u2 = make_float2(uu[c], uu[c + 1]), v2 = make_float2(vv[c], vv[c + 1]);
+            auto X = [&](int k) { return make_float2(xw[k][c], xw[k][c + 1]); };
+            auto Y = [&](int k) { return make_float2(yw[c + k], yw[c + 1 + k]); };
+            auto bc = [](float a) { return make_float2(a, a); };
+            auto div2 = [&](float2 x, float s, float rcp) {
+                const float2 q = __fmul2_rn(x, bc(rcp));
+                const float2 rem = __ffma2_rn(q, bc(-s), x);
+                return __ffma2_rn(rem, bc(rcp), q);
+            };
+            float2 acc = bc(0.f);
             if (p.rhs_id & PPNN_RHS_ADV) {
-                float fx = 0.f, fy = 0.f;
+                float2 fx = bc(0.f), fy = bc(0.f);
                 if (p.adv_upwind) {
                     // Upwind1: the forward filter is zero left of the centre, the backward one right of
                     // it (operators.py:211-218) -- the zero taps add nothing and are skipped
                     constexpr int C = (K - 1) / 2;
-                    float bx = 0.f, by = 0.f;
+                    float2 bx = bc(0.f), by = bc(0.f);
 #pragma unroll
-                    for (int k = C; k < K; ++k) { fx += p.aa[k] * xw[k][c]; fy += p.aa[k] * yw[c + k]; }
+                    for (int k = C; k < K; ++k) { fx = __ffma2_rn(bc(p.aa[k]), X(k), fx); fy = __ffma2_rn(bc(p.aa[k]), Y(k), fy); }
 #pragma unroll
-                    for (int k = 0; k <= C; ++k) { bx += p.ab[k] * xw[k][c]; by += p.ab[k] * yw[c + k]; }
-                    const float c1 = xw[C][c], c2 = yw[c + C];
-                    fx = c1 <= 0.f ? fx : (c1 > 0.f ? bx : 0.f);
-                    fy = c2 <= 0.f ? fy : (c2 > 0.f ? by : 0.f);
+                    for (int k = 0; k <= C; ++k) { bx = __ffma2_rn(bc(p.ab[k]), X(k), bx); by = __ffma2_rn(bc(p.ab[k]), Y(k), by); }
+                    const float2 c1 = X(C), c2 = Y(C);
+                    fx.x = c1.x <= 0.f ? fx.x : (c1.x > 0.f ? bx.x : 0.f); fx.y = c1.y <= 0.f ? fx.y : (c1.y > 0.f ? bx.y : 0.f);
+                    fy.x = c2.x <= 0.f ? fy.x : (c2.x > 0.f ? by.x : 0.f); fy.y = c2.y <= 0.f ? fy.y : (c2.y > 0.f ? by.y : 0.f);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) { fx += p.aa[k] * xw[k][c]; fy += p.aa[k] * yw[c + k]; }
+                    for (int k = 0; k < K; ++k) { fx = __ffma2_rn(bc(p.aa[k]), X(k), fx); fy = __ffma2_rn(bc(p.aa[k]), Y(k), fy); }
                 }
-                acc = div_by(-u1 * fx, p.dx, p.rdx) - div_by(v1 * fy, p.dy, p.rdy);
+                // div_by(-u1 * fx) - div_by(v1 * fy); a - b as fma(b, -1, a): one rounding, same signed zeros
+                const float2 un = make_float2(-u2.x, -u2.y);
+                acc = __ffma2_rn(div2(__fmul2_rn(v2, fy), p.dy, p.rdy), bc(-1.f), div2(__fmul2_rn(un, fx), p.dx, p.rdx));
             }
             if (p.rhs_id & PPNN_RHS_DIFF) {
-                float lx = 0.f, ly = 0.f;
+                float2 lx = bc(0.f), ly = bc(0.f);
 #pragma unroll
-                for (int k = 0; k < K; ++k) { lx += p.d[k] * xw[k][c]; ly += p.d[k] * yw[c + k]; }
-                const float lap = mu * (div_by(lx, p.dx2, p.rdx2) + div_by(ly, p.dy2, p.rdy2));
-                acc = (p.rhs_id & PPNN_RHS_ADV) ? acc + lap : lap;
+                for (int k = 0; k < K; ++k) { lx = __ffma2_rn(bc(p.d[k]), X(k), lx); ly = __ffma2_rn(bc(p.d[k]), Y(k), ly); }
+                const float2 lap = __fmul2_rn(bc(mu), __fadd2_rn(div2(lx, p.dx2, p.rdx2), div2(ly, p.dy2, p.rdy2)));
+                acc = (p.rhs_id & PPNN_RHS_ADV) ? __fadd2_rn(acc, lap) : lap;
             }
-            res[c] = add_reaction(acc, p.rhs_id & ~3, u1, v1);
+            res[c] = add_reaction(acc.x, p.rhs_id & ~3, u2.x, v2.x);
+            res[c + 1] = add_reaction(acc.y, p.rhs_id & ~3, u2.y, v2.y);
         }
         const size_t o = ((size_t)b * p.H + i0 + r) * p.W + jg;
         asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + o), "f"(res[0]), "f"(res[1]), "f"(res[2]), "f"(res[3]) : "memory");

@@ -343,7 +343,9 @@ static int launch_rhs2d(const RhsParams& p, int B, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(rhs2d_tile_kernel<K, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         dim3 grid((p.W + kRTileCols - 1) / kRTileCols, (p.H + TR - 1) / TR, (unsigned)B);
-        rhs2d_tile_kernel<K, TR><<<grid, 128, smem, s>>>(p, p.ay + (size_t)B * p.H * (p.W + 2 * p.halo));
+        // a thread owns 4 columns: grids narrower than the 512-column tile launch only the warps that have some
+        const int threads = p.W >= kRTileCols ? 128 : ((p.W / 4 + 31) & ~31);
+        rhs2d_tile_kernel<K, TR><<<grid, threads, smem, s>>>(p, p.ay + (size_t)B * p.H * (p.W + 2 * p.halo));
         return launch_status();
     }
     dim3 grid((p.W + 127) / 128, (p.H + kRhsRows - 1) / kRhsRows, (unsigned)B);

@@ -391,6 +391,12 @@ static int fill_fine(FineParams* p, const float* u, const float* v, const float*
 
 using namespace ppnn;
 
+#ifdef PPNN_TRACE
+extern "C" int ppnn_trace_read_fine(unsigned long long* host, long n) {
+    return (int)cudaMemcpyFromSymbol(host, ppnn::g_trace_fine, (size_t)n * sizeof(unsigned long long));
+}
+#endif
+
 extern "C" int ppnn_fine_burgers_step(const float* u, const float* v, const float* mu,
                                       float* u_out, float* v_out, int B, int H, int W,
                                       int endpoint, int mode, int adv_accuracy, int diff_accuracy,

@@ -50,6 +50,15 @@ struct BandCursor {
     __device__ __forceinline__ int first_row() const { return r0 - kTmaRows + c * kTmaRows; }   // unwrapped
 };
 
+#ifdef PPNN_TRACE
+// dev-only CTA timeline (tools/trace_fine.py); never in the shipped library
+__device__ unsigned long long g_trace_fine[4 * 1024];
+__device__ __forceinline__ unsigned long long gtime_fine() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PPNN_FSTAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_trace_fine[4 * blockIdx.x + (k)] = gtime_fine(); } while (0)
+#else
+#define PPNN_FSTAMP(k) do { } while (0)
+#endif
+
 template <int HL, int MODE, int WC>
 __global__ void __launch_bounds__(576)
 fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
@@ -69,6 +78,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == pl.cwarps;
+    PPNN_FSTAMP(0);
     const size_t plane = (size_t)p.H * W;
     const long g0 = (long)blockIdx.x * pl.units_per_cta;
     const long g1 = min(g0 + pl.units_per_cta, pl.total_units);
@@ -246,6 +256,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
         int s1 = s0; uint32_t ph1 = ph0; next_slot(s1, ph1);
         mbar_wait(&ready[s0], ph0);
         mbar_wait(&ready[s1], ph1);
+        if (g == g0) PPNN_FSTAMP(1);
         float2 wu[2 * HL + R], wv[VWIN ? 2 * HL + R : 1];
 #pragma unroll
         for (int k = 0; k < HL; ++k) {
@@ -321,6 +332,7 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
         slot = sn; phase = phn;
         g += r1 - r0;
     }
+    PPNN_FSTAMP(2);
 }
 
 template <int HL, int MODE, int WC>

@@ -292,14 +292,16 @@ dataset_pass_kernel(const CoarseParams p, const DatasetIO io, const StepPlan pl,
                         return h[o] * pw.w[r][0] + h[o + 1] * pw.w[r][1] + h[o + 2] * pw.w[r][2] + h[o + 3] * pw.w[r][3];
                     };
 #ifdef PPNN_DBG_NOCOMPUTE
-                    if (false) {
-                    } else if (true) {
-                        A_p.x += su[0];
+                    // dev-only timing build (profiles/r2_cta_timelines.txt): consumers only wait for and release the bands
+                    constexpr bool kCompute = false;
+                    A_p.x += su[0];
 #else
-                    if constexpr (EMIT) {
+                    constexpr bool kCompute = true;
+#endif
+                    if constexpr (!kCompute) {
+                    } else if constexpr (EMIT) {
 #pragma unroll
                         for (int q = 0; q < R; ++q) emit(q, pde_row(q), false);
-#endif
                     } else {
                         // statistics: two rows per packed fp32x2 instruction (8 issue slots per row pair
                         // instead of 16 for the two differences and six accumulations)
@@ -484,7 +486,7 @@ static int run_dataset(const ppnn_coarse_cfg* cfg, DatasetIO io, long B, bool em
     const size_t smem = tables + (size_t)((3 * p.NH * p.NW + 3) & ~3) * sizeof(float) +
                         (size_t)nst * 2 * 2 * lay.ustage * sizeof(float);
     if (smem > 200 * 1024) return PPNN_E_TOOBIG;
-#ifdef PPNN_DBG_SMEM
+#ifdef PPNN_DBG_SMEM      // dev-only timing build: padded shared memory => one CTA per SM (profiles/r2_cta_timelines.txt)
     const size_t smem_launch = PPNN_DBG_SMEM;
 #else
     const size_t smem_launch = smem;

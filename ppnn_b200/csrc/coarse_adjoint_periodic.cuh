@@ -164,7 +164,6 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
     __shared__ __align__(8) uint64_t empty[kAdjStages];
     __shared__ __align__(8) uint64_t cbar;                       // arrival of the saved coarse state
     __shared__ float red[32];
-    __shared__ float mu_partial;
 
     const int b = blockIdx.x >> 1, f = blockIdx.x & 1;           // f == rank in the cluster
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -402,30 +401,19 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
     __syncthreads();
     PPNN_STAMP(2);
 
-    // ---- grad_mu partial of this field (needs only local data) ----
     const float* own = f ? cv : cu;
     const bool fast = p.adv_n == 2 && p.diff_n == 3;
+    const bool want_mu = a.gmu && (rid_own & PPNN_RHS_DIFF);
+    // grad_mu partial of this field (needs only local data): summed inside the scatter loop below -- or, when the
+    // fields are coupled, here, where it fills the wait for the sibling CTA at the cluster barrier; reduced at the end
     float part = 0.f;
-    if (a.gmu && (rid_own & PPNN_RHS_DIFF)) {
+    if (want_mu && both) {
         for (int idx = tid; idx < NN2; idx += kAdjThreads) {
             const int I = small_div(idx, NC), J = idx - I * NC;
             part += (fast ? laplace_t<3>(p, own, I, J)
                           : central_x(p, own, I, J) * p.rdx2 + central_y(p, own, I, J) * p.rdy2) * q[idx];
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (warp == 0) {
-        float v = lane < (kAdjThreads >> 5) ? red[lane] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) mu_partial = v;
-    }
-    __syncthreads();
-    // grad_mu[b] = partial(u) + partial(v): the launcher zeroed it; a sum of two floats does not depend on order
-    if (tid == 0 && a.gmu) atomicAdd(a.gmu + b, mu_partial);
 
     // ---- exchange of the coarse cotangents (only when a right-hand side couples the fields) ----
     const float* q_oth = A;
@@ -442,6 +430,9 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
     for (int idx = tid; idx < NN2; idx += kAdjThreads) {
         const int I = small_div(idx, NC), J = idx - I * NC;
         const float q_own = q[idx];
+        // (same per-thread order of terms as the separate pass)
+        if (want_mu && !both) part += (fast ? laplace_t<3>(p, own, I, J)
+                                   : central_x(p, own, I, J) * p.rdx2 + central_y(p, own, I, J) * p.rdy2) * q_own;
         float cot = fast ? stencil_adjoint_t<2, 3>(p, rid_own, own, cu, cv, q, I, J, mu)
                          : stencil_adjoint(p, rid_own, own, cu, cv, q, I, J, mu);
         if (both) {
@@ -471,6 +462,20 @@ coarse_adjoint_periodic_kernel(const CoarseParams p, const AdjParams a, const Ph
             float* o2 = o + (size_t)t.di * F;
             atomicAdd(o2, t.li * w0 * cot);
             if (t.lj != 0.f) atomicAdd(o2 + t.dj, t.li * t.lj * cot);
+        }
+    }
+    // grad_mu[b] = partial(u) + partial(v): fixed-order sum inside the CTA (lanes, then warps); the launcher zeroed
+    // the entry and a sum of two floats does not depend on the order of the two atomics
+    if (a.gmu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (warp == 0) {
+            float v = lane < (kAdjThreads >> 5) ? red[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(a.gmu + b, v);
         }
     }
     PPNN_STAMP(4);

@@ -1025,6 +1025,46 @@ def test_tiled_y_stencils_and_fused_rhs(pk, b, h, w):
             assert_parity(ours.cpu(), ref, TOL, f"{name} {aa}/{da} {b}x{h}x{w}")
 
 
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+def test_plane_kernels_stay_inside_their_buffers(pk, offset):
+    """Whole-plane Tier-A kernels (rhs2d_plane_kernel, bicubic_up_plane_kernel) on operands that start at every
+    4-byte phase inside NaN-filled buffers: same results as on ordinary tensors (a NaN read from a guard word would
+    surface in the output), guard words untouched."""
+    import ctypes as C
+    L = pk["lib"]
+    lib = L.load()
+    gen = torch.Generator().manual_seed(40 + offset)
+    ops, rhs, M = pk["ops"], pk["rhs"], pk["mesh"]
+    # fused rhs on a coarse grid, halo 1 and halo 3
+    for (aa, da, n) in ((1, 2, 32), (3, 6, 12)):
+        h = aa
+        u1 = torch.randn(3, 1, n, n, generator=gen).cuda()
+        v1 = torch.randn(3, 1, n, n, generator=gen).cuda()
+        mu = torch.tensor([0.02, 0.045, 0.07]).reshape(-1, 1, 1, 1).cuda()
+        ax, ay = O.wrap_x(u1, h), O.wrap_y(u1, h)
+        dudx, dudy, d2x, d2y = ops.dudx_2D(accuracy=aa), ops.dudy_2D(accuracy=aa), ops.d2udx2_2D(accuracy=da), ops.d2udy2_2D(accuracy=da)
+        ref = rhs.burgers2DFu(u1, v1, mu, dudx, dudy, d2x, d2y, ax, ay, 0.1, 0.08, 0.01, 0.0064)
+        (u1e, ub), (v1e, vb), (axe, axb), (aye, ayb) = (_embedded(t, offset) for t in (u1, v1, ax, ay))
+        oe, ob = _embedded(torch.zeros_like(ref), offset)
+        muv = mu.reshape(-1).contiguous()
+        L.check(lib.ppnn_rhs2d_fwd(u1e.data_ptr(), v1e.data_ptr(), muv.data_ptr(), axe.data_ptr(), aye.data_ptr(), oe.data_ptr(),
+                                   3, n, n, h, rhs.RHS_IDS["burgers2DFu"],
+                                   ops.dudx_2D(accuracy=aa)._scheme_id, aa, ops.d2udx2_2D(accuracy=da)._scheme_id, da,
+                                   0.1, 0.08, 0.01, 0.0064, L.stream()), "rhs2d")
+        assert torch.equal(oe, ref), f"rhs acc {aa}/{da} offset {offset}"
+        for v, b in ((u1e, ub), (v1e, vb), (axe, axb), (aye, ayb), (oe, ob)):
+            assert _guards_intact(v, b)
+    # bicubic up-sampling of small planes (257 output columns: rows on every 4-byte phase)
+    for (c, f) in ((33, 257), (9, 65)):
+        x = torch.randn(3, 1, c, c, generator=gen).cuda()
+        ref = M(f, c, dim=2).up(x)
+        xe, xb = _embedded(x, offset)
+        oe, ob = _embedded(torch.zeros_like(ref), offset)
+        L.check(lib.ppnn_resample_fwd(xe.data_ptr(), oe.data_ptr(), 3, c, c, f, f, L.BICUBIC, 1, L.stream()), "up")
+        assert torch.equal(oe, ref), f"up {c}->{f} offset {offset}"
+        assert _guards_intact(xe, xb) and _guards_intact(oe, ob)
+
+
 def test_tiled_kernels_at_the_end_of_an_allocation(pk):
     """The staged copies start at the enclosing 16-byte boundary and are clamped at the end of the
     tensor: inputs that end exactly at the end of their allocation, NaN guard bands around them."""

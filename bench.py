@@ -419,6 +419,53 @@ def train_leg(torch, dist, dev, world, rank, local, timed, L):
     return out
 
 
+def tier_a_leg(torch, dev, timed, fused_step):
+    """pde_du three ways at the rollout batch (12) and a precompute-sized batch (2160): the closure of
+    train2D.py:38-79 bound to (a) ppnn_b200's drop-in operators / rhs / mesh_convertor (Tier A: one kernel per
+    reference call, the reference's own torch.cat pads), (b) the same ATen ops the reference runs on a GPU today
+    (true fp32: cuDNN TF32 off), (c) the fused kernel (Tier B)."""
+    import ppnn_b200.operators as ops
+    import ppnn_b200.rhs as rhs
+    from ppnn_b200.utility.utils import mesh_convertor
+    F, C = CASE["fine"], CASE["coarse"]
+    dx = CASE["length"] / (C - 1)
+    dy, dx2, dy2, dt = dx, dx * dx, dx * dx, CASE["dt"]
+    rhsu, rhsv = getattr(rhs, CASE["rhsu"]), getattr(rhs, CASE["rhsv"])
+    d2udx2, d2udy2 = ops.d2udx2_2D(accuracy=2, device=dev), ops.d2udy2_2D(accuracy=2, device=dev)
+    dudx, dudy = ops.dudx_2D(accuracy=1, device=dev), ops.dudy_2D(accuracy=1, device=dev)
+    mcvter = mesh_convertor(F, C, dim=2)
+
+    def padbcx(t):
+        return torch.cat((t[:, :, -1:], t, t[:, :, :1]), dim=2)
+
+    def padbcy(t):
+        return torch.cat((t[:, :, :, -1:], t, t[:, :, :, :1]), dim=3)
+
+    def padBC_rd(t):
+        tmp = torch.cat((t, t[:, :, :, :1]), dim=3)
+        return torch.cat((tmp, tmp[:, :, :1]), dim=2)
+
+    def pde_du(u, mu):
+        u1 = mcvter.down(u[:, :1])[:, :, :-1, :-1]
+        v1 = mcvter.down(u[:, 1:])[:, :, :-1, :-1]
+        ux, uy, vx, vy = padbcx(u1), padbcy(u1), padbcx(v1), padbcy(v1)
+        return torch.cat((mcvter.up(padBC_rd(dt * rhsu(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, ux, uy, dx, dy, dx2, dy2))),
+                          mcvter.up(padBC_rd(dt * rhsv(u1, v1, mu, dudx, dudy, d2udx2, d2udy2, vx, vy, dx, dy, dx2, dy2)))),
+                         dim=1)
+
+    out = {"note": "ms per pde_du call; tier_a = drop-in modules behind the unchanged closure, tier_b = fused kernel"}
+    with torch.no_grad():
+        for B in (12, 2160):
+            u = synth_fields(B, F, dev, 21)
+            mu = make_mu(B, dev).reshape(-1, 1, 1, 1)
+            ya, yb = pde_du(u, mu), fused_step.pde_du(u, mu)
+            err = float((ya - yb).norm() / yb.norm())
+            out[f"B{B}"] = {"tier_a_ms": timed(lambda: pde_du(u, mu), 10, 3), "tier_b_ms": timed(lambda: fused_step.pde_du(u, mu), 10, 3),
+                            "tier_a_vs_tier_b_rel_l2": err}
+            del u, ya, yb
+    return out
+
+
 def datagen_leg(torch, dist, dev, world, rank, local, max_over_ranks, barrier, link=None):
     """BASELINE configs[3]: the fine-grid Burgers generator (operators.py:403-492) at the reference's LENGTH
     (20 001 steps, snapshot every 200 => 101 snapshots), 1025^2 (the reference's duplicated-endpoint convention at
@@ -711,6 +758,13 @@ def run_ours(args):
             del ku, kw, hb
         except Exception as exc:
             extras["onchip_solvers_error"] = repr(exc)[:300]
+
+        # Tier A: the pde_du closure of train2D.py:38-79 re-typed around the drop-in modules -- what an UNCHANGED
+        # reference script executes -- next to the same ATen op sequence on the GPU and the fused kernel
+        try:
+            extras["tier_a_pde_du_chain_RD_pPDE"] = tier_a_leg(torch, dev, timed, step)
+        except Exception as exc:
+            extras["tier_a_error"] = repr(exc)[:300]
 
         try:
             if not args.no_legs:

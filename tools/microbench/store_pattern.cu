@@ -13,6 +13,13 @@ __global__ void __launch_bounds__(288) kA(float* out, int cs) {
     float* o = out + (size_t)blockIdx.x * PL + j;
     for (int i = 0; i < F; ++i, o += F) { const float v = (float)(i + j); if (cs) __stcs(o, v); else *o = v; }
 }
+// A with only the 256 columns of the eight full warps (no lone 4-byte store per row), and with a row pitch of 256
+// floats (every warp store a whole aligned line): separates the access ORDER from the ALIGNMENT
+__global__ void __launch_bounds__(256) kA2(float* out, int pitch) {
+    const int j = threadIdx.x;
+    float* o = out + (size_t)blockIdx.x * PL + j;
+    for (int i = 0; i < 256; ++i, o += pitch) *o = (float)(i + j);
+}
 __global__ void __launch_bounds__(288) kB(float* out, size_t total) {
     // plane per CTA, lines of 32 floats aligned to 128 bytes of the whole buffer
     const size_t lo = (size_t)blockIdx.x * PL, hi = lo + PL;
@@ -44,6 +51,8 @@ int main() {
     t = timeit([&] { kA<<<planes, 288>>>(d, 1); }); printf("A  thread = column, streaming stores : %.4f ms  %.0f GB/s\n", t, gb / t * 1e3);
     t = timeit([&] { kA<<<planes, 288>>>(d, 0); }); printf("A  thread = column, write-back stores: %.4f ms  %.0f GB/s\n", t, gb / t * 1e3);
     t = timeit([&] { kA<<<planes, 288>>>(d + 1, 0); }); printf("A  the same, buffer shifted by 4 bytes : %.4f ms  %.0f GB/s\n", t, gb / t * 1e3);
+    t = timeit([&] { kA2<<<planes, 256>>>(d, 257); }); printf("A2 256 columns of 257-float rows       : %.4f ms  %.0f GB/s\n", t, planes * 65536.0 * 4 / 1e9 / t * 1e3);
+    t = timeit([&] { kA2<<<planes, 256>>>(d, 256); }); printf("A3 256 columns of 256-float rows       : %.4f ms  %.0f GB/s\n", t, planes * 65536.0 * 4 / 1e9 / t * 1e3);
     t = timeit([&] { kB<<<planes, 288>>>(d, total); }); printf("B  aligned 128-byte lines, scalar    : %.4f ms  %.0f GB/s\n", t, gb / t * 1e3);
     t = timeit([&] { kC<<<148 * 16, 256>>>((float4*)d, total / 4); }); printf("C  aligned float4                    : %.4f ms  %.0f GB/s\n", t, gb / t * 1e3);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));

@@ -144,9 +144,12 @@ constexpr int kUpBand = 64;      // output rows per CTA
 // Write-only kernels on rows of 257 floats run at the store path's rate, not the HBM's: rows start on every 4-byte
 // phase, so a warp's 128-byte store touches five 32-byte sectors, two of them partially.  Ordinary (write-back)
 // stores: in the whole-plane kernel the streaming hint costs 20 % (0.207 vs 0.169 ms for 2160 planes 33^2 -> 257^2).
-// Tried and dropped (same box): rows staged in shared memory and written as 16-byte-aligned vectors (0.31 ms: one
-// barrier per 4 rows), the plane as a linear array of aligned float4 with the H pass from a W-interpolated copy
-// of the source in shared memory (0.27 ms: ~18 instructions per output).
+// A bare store microbenchmark (tools/microbench/store_pattern.cu) puts this layout at 2.8 TB/s and aligned lines of the
+// linear plane at 6.2 - 6.8 TB/s.  Tried and dropped (same box, profiles/r2_mesh_up_ab.txt): rows staged in shared
+// memory and written as 16-byte-aligned vectors -- 0.31 ms with one barrier per 4 rows, 0.21 ms with 8 rows per band
+// and full occupancy (ncu: issue-bound, 39 instructions per row and warp), 0.19 ms with two columns per thread;
+// the plane as a linear array of aligned float4 with the H pass from a W-interpolated copy of the source in shared
+// memory (0.27 ms: ~18 instructions per output).  The thread-per-column kernel below stays at 0.17 ms.
 __device__ __forceinline__ void up_store(float* p, float v) { *p = v; }
 
 __global__ void __launch_bounds__(128)

@@ -187,6 +187,9 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
     const int offU = FRONT + colA, offV = band_floats + FRONT + colA;
     int slot = 0; uint32_t phase = 0;
     auto next_slot = [&](int& sl, uint32_t& ph) { if (++sl == pl.ring) { sl = 0; ph ^= 1; } };
+#ifdef PPNN_FINE_NOSTORE
+    float sink = 0.f;
+#endif
 
     // Odd widths (W = 2^k + 1) leave the last consumer warp with ONE live column.  Walking the rows with a
     // register window like the others would cost a full warp's instruction stream for it (1/17 of the issue
@@ -311,10 +314,14 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
                 const float2 vcen = VWIN ? wv[HL + q] : make_float2(vr[0], vr[dB]);
                 float2 unew, vnew;
                 fine_point_update<HL, MODE, true>(p, mu, c, vcen, wu + q, wv + (VWIN ? q : 0), yu, yv, unew, vnew);
+#ifdef PPNN_FINE_NOSTORE      // dev-only timing build: the arithmetic stays alive, nothing is written
+                sink += unew.x + vnew.x + unew.y + vnew.y;
+#else
                 if (active && r0 + n * R + q < r1) {
                     ouA[(size_t)q * W] = unew.x; ovA[(size_t)q * W] = vnew.x;
                     if (hasB) { ouA[(size_t)q * W + dB] = unew.y; ovA[(size_t)q * W + dB] = vnew.y; }
                 }
+#endif
             }
 #pragma unroll
             for (int k = 0; k < 2 * HL; ++k) {
@@ -332,6 +339,9 @@ fine_step_ep_kernel(const FineParams p, const FineEpPlan pl) {
         slot = sn; phase = phn;
         g += r1 - r0;
     }
+#ifdef PPNN_FINE_NOSTORE
+    if (sink == 12345.678f) p.uo[0] = sink;
+#endif
     PPNN_FSTAMP(2);
 }
 
